@@ -1,0 +1,289 @@
+// C ABI of libmagi_b200.so (see include/magi_b200.h for the reference interfaces each entry point replaces).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include "magi_common.cuh"
+#include "magi_internal.cuh"
+
+using namespace magi;
+
+static thread_local std::string g_last_error;
+
+namespace magi {
+int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_error(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return MAGI_ERR_CUDA;
+}
+}  // namespace magi
+
+#define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_error(e__, what); } while (0)
+
+extern "C" const char* magi_last_error(void) { return g_last_error.c_str(); }
+extern "C" int magi_version(void) { return 100; }
+
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
+extern "C" int magi_destroy(magi_handle* h) {
+    if (!h) return MAGI_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 3; ++i) free_dev(h->d_band[i]);
+    for (int i = 0; i < 7; ++i) free_dev(h->d_dense[i]);
+    free_dev(h->d_fragtab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
+    free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
+    free_dev(h->d_dense_work);
+    hmc_free(h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MAGI_OK;
+}
+
+extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
+    if (!cfg || !out) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: null argument");
+    *out = nullptr;
+    if (cfg->n_times < 1 || cfg->n_dims < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: n_times and n_dims must be >= 1");
+    if (!cfg->tvec || !cfg->yobs || !cfg->sigma_init || !cfg->prior_temperature)
+        return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: tvec, yobs, sigma_init and prior_temperature are required");
+    int mD = 0, mK = 0;
+    if (cfg->ode_model_id == MAGI_MODEL_L96) { mD = cfg->n_dims; mK = 1; }
+    else if (!model_dims(cfg->ode_model_id, mD, mK)) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: unknown ode_model_id");
+    if (mD != cfg->n_dims || mK != cfg->n_params_ode) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "magi_create: model %d has D=%d, k=%d but config says D=%d, k=%d", cfg->ode_model_id, mD, mK, cfg->n_dims, cfg->n_params_ode);
+        return set_error(MAGI_ERR_INVALID_ARGUMENT, buf);
+    }
+    if (cfg->setup_mode != MAGI_SETUP_INJECT) {
+        if (!cfg->phi) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: phi is required unless setup_mode is MAGI_SETUP_INJECT");
+        if (cfg->kernel_id != MAGI_KERNEL_MATERN52 && cfg->kernel_id != MAGI_KERNEL_RBF)
+            return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: unknown kernel_id");
+        for (int d = 0; d < cfg->n_dims; ++d) {   // src/MagiJl.jl:469-472
+            double var = cfg->phi[2 * d], len = cfg->phi[2 * d + 1];
+            if (!std::isfinite(var) || var <= 0 || !std::isfinite(len) || len <= 0)
+                return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: invalid GP hyperparameters (variance and lengthscale must be finite and > 0)");
+        }
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return set_error(MAGI_ERR_CUDA, "magi_create: no CUDA device available (libmagi_b200 has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device), "cudaGetDeviceProperties");
+    if (prop.major != 10) return set_error(MAGI_ERR_UNSUPPORTED, "magi_create: libmagi_b200 is built for sm_100a (B200) only");
+
+    magi_handle* h = new (std::nothrow) magi_handle();
+    if (!h) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: out of host memory");
+    h->n = cfg->n_times; h->D = cfg->n_dims; h->K = cfg->n_params_ode;
+    h->sigma_is_fixed = cfg->sigma_is_fixed ? 1 : 0;
+    h->P = h->n * h->D + h->K + (h->sigma_is_fixed ? 0 : h->D);
+    int b = cfg->bandsize;
+    if (b > h->n - 1) b = h->n - 1;             // src/MagiJl.jl:459-460
+    if (b < 0) b = 0;
+    h->b = b;
+    h->kernel_id = cfg->kernel_id; h->model = cfg->ode_model_id; h->setup_mode = cfg->setup_mode;
+    h->device = cfg->device; h->jitter = cfg->jitter;
+    h->tvec.assign(cfg->tvec, cfg->tvec + h->n);
+    if (cfg->phi) h->phi.assign(cfg->phi, cfg->phi + 2 * h->D);
+    h->yobs.assign(cfg->yobs, cfg->yobs + (size_t)h->n * h->D);
+    h->sigma_init.assign(cfg->sigma_init, cfg->sigma_init + h->D);
+    for (int i = 0; i < 3; ++i) h->beta[i] = cfg->prior_temperature[i];
+    h->sigma_invalid = 0;
+    if (h->sigma_is_fixed)
+        for (int d = 0; d < h->D; ++d)
+            if (!std::isfinite(h->sigma_init[d]) || h->sigma_init[d] <= 0) h->sigma_invalid = 1;   // interface.jl:192
+    h->geom = band_geom(h->n, h->b);
+    h->smem_limit = (int)prop.sharedMemPerBlockOptin - 1024;
+    h->sm_count = prop.multiProcessorCount;
+    h->repaired_c.assign(h->D, 0); h->repaired_k.assign(h->D, 0);
+    h->band_set.assign((size_t)3 * h->D, 0);
+
+    int rc = MAGI_OK;
+    auto fail = [&](int code) { magi_destroy(h); return code; };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaStreamCreate failed"));
+    const size_t tab = (size_t)(2 * h->b + 1) * h->n;
+    for (int i = 0; i < 3; ++i) {
+        if (cudaMalloc(&h->d_band[i], sizeof(double) * tab * h->D) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc band tables failed"));
+        cudaMemsetAsync(h->d_band[i], 0, sizeof(double) * tab * h->D, h->stream);
+    }
+    std::vector<int> nobs(h->D, 0);
+    for (int d = 0; d < h->D; ++d)
+        for (int i = 0; i < h->n; ++i) nobs[d] += std::isfinite(h->yobs[(size_t)d * h->n + i]) ? 1 : 0;
+    if (cudaMalloc(&h->d_yobs, sizeof(double) * h->n * h->D) != cudaSuccess || cudaMalloc(&h->d_nobs, sizeof(int) * h->D) != cudaSuccess ||
+        cudaMalloc(&h->d_sigma_init, sizeof(double) * h->D) != cudaSuccess)
+        return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc failed"));
+    cudaMemcpyAsync(h->d_yobs, h->yobs.data(), sizeof(double) * h->n * h->D, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_nobs, nobs.data(), sizeof(int) * h->D, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_sigma_init, h->sigma_init.data(), sizeof(double) * h->D, cudaMemcpyHostToDevice, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "upload failed"));
+
+    h->dense_mode = (h->geom.HB > kMaxHB) || h->model == MAGI_MODEL_L96;
+    if (!h->dense_mode) {
+        size_t fsz = (size_t)4 * h->D * h->geom.NT * h->geom.NCH * 32;
+        if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
+        banded_pick_config(h->D, h->K, h->geom.NT, h->smem_limit, h->G, h->DW, h->scratch_in_smem, h->smem_bytes);
+    }
+    if (h->setup_mode != MAGI_SETUP_INJECT) {
+        rc = run_device_setup(h);
+        if (rc != MAGI_OK) return fail(rc);
+    }
+    if (cfg->max_chains > 0) {
+        rc = ensure_capacity(h, cfg->max_chains);
+        if (rc != MAGI_OK) return fail(rc);
+    }
+    *out = h;
+    return MAGI_OK;
+}
+
+namespace magi {
+
+int ensure_capacity(magi_handle* h, int n_chains) {
+    if ((size_t)n_chains <= h->cap_chains) return MAGI_OK;
+    free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad);
+    h->d_params = h->d_ll = h->d_grad = nullptr; h->cap_chains = 0;
+    size_t cap = (size_t)n_chains;
+    CK(cudaMalloc(&h->d_params, sizeof(double) * cap * h->P), "cudaMalloc params staging");
+    CK(cudaMalloc(&h->d_grad, sizeof(double) * cap * h->P), "cudaMalloc grad staging");
+    CK(cudaMalloc(&h->d_ll, sizeof(double) * cap), "cudaMalloc ll staging");
+    h->cap_chains = cap;
+    return MAGI_OK;
+}
+
+static int ensure_scratch(magi_handle* h, int n_chains) {
+    if (h->dense_mode || h->scratch_in_smem) return MAGI_OK;
+    size_t blocks = ((size_t)n_chains + h->G * 8 - 1) / (h->G * 8);
+    size_t need = blocks * banded_scratch_doubles_per_cta(h->G, h->D, h->geom.NT);
+    if (need <= h->scratch_cap) return MAGI_OK;
+    free_dev(h->d_scratch); h->d_scratch = nullptr; h->scratch_cap = 0;
+    CK(cudaMalloc(&h->d_scratch, sizeof(double) * need), "cudaMalloc Ke scratch");
+    h->scratch_cap = need;
+    return MAGI_OK;
+}
+
+int refresh_fragtab(magi_handle* h, cudaStream_t st) {
+    if (!h->frag_dirty || h->dense_mode) return MAGI_OK;
+    CK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], h->d_fragtab, h->n, h->b, h->D, st), "build_fragtab");
+    h->launches++;
+    h->frag_dirty = false;
+    return MAGI_OK;
+}
+
+// core evaluation on device pointers (chain-contiguous, pitch doubles per chain)
+int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st) {
+    if (n_chains <= 0) return MAGI_OK;
+    if (!h->tables_ready) return set_error(MAGI_ERR_NOT_READY, "band tables are neither built nor fully injected (magi_set_band_tables for every dim and table)");
+    if (h->dense_mode) return eval_dense_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
+    int rc = refresh_fragtab(h, st);
+    if (rc) return rc;
+    rc = ensure_scratch(h, n_chains);
+    if (rc) return rc;
+    BandedArgs a;
+    a.n = h->n; a.D = h->D; a.K = h->K; a.P = h->P; a.n_chains = n_chains; a.NT = h->geom.NT; a.G = h->G;
+    a.sigma_is_fixed = h->sigma_is_fixed; a.sigma_invalid = h->sigma_invalid; a.scratch_in_smem = h->scratch_in_smem;
+    a.pitch = pitch; a.params = params_dev; a.ll = ll_dev; a.grad = grad_dev;
+    a.fragtab = h->d_fragtab; a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
+    for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
+    a.scratch = h->d_scratch;
+    CK(launch_banded_cfg(h->model, a, h->geom.HB, h->DW, h->smem_bytes, st), "banded_logpost_kernel launch");
+    h->launches++;
+    return MAGI_OK;
+}
+
+}  // namespace magi
+
+extern "C" int magi_dimension(const magi_handle* h) { return h ? h->P : -1; }
+extern "C" int magi_capabilities_order(const magi_handle* h) { (void)h; return 1; }
+extern "C" long long magi_launch_count(const magi_handle* h) { return h ? h->launches : -1; }
+
+extern "C" int magi_logdensity_and_gradient_batched_dev(magi_handle* h, int n_chains, const double* params_dev, double* ll_dev,
+                                                        double* grad_dev, int layout, void* stream) {
+    if (!h || !params_dev || !ll_dev) return set_error(MAGI_ERR_INVALID_ARGUMENT, "batched_dev: null argument");
+    if (layout != MAGI_LAYOUT_CHAIN_CONTIGUOUS) return set_error(MAGI_ERR_UNSUPPORTED, "batched_dev: unknown layout");
+    if (n_chains < 0) return set_error(MAGI_ERR_INVALID_ARGUMENT, "batched_dev: n_chains < 0");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    return eval_dev(h, n_chains, params_dev, h->P, ll_dev, grad_dev, (cudaStream_t)stream);
+}
+
+extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains, const double* params, double* ll, double* grad) {
+    if (!h || !params || !ll) return set_error(MAGI_ERR_INVALID_ARGUMENT, "batched: null argument");
+    if (n_chains < 0) return set_error(MAGI_ERR_INVALID_ARGUMENT, "batched: n_chains < 0");
+    if (n_chains == 0) return MAGI_OK;
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    int rc = ensure_capacity(h, n_chains);
+    if (rc) return rc;
+    const size_t nb = sizeof(double) * (size_t)n_chains * h->P;
+    CK(cudaMemcpyAsync(h->d_params, params, nb, cudaMemcpyHostToDevice, h->stream), "H2D params");
+    rc = eval_dev(h, n_chains, h->d_params, h->P, h->d_ll, grad ? h->d_grad : nullptr, h->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ll, h->d_ll, sizeof(double) * n_chains, cudaMemcpyDeviceToHost, h->stream), "D2H ll");
+    if (grad) CK(cudaMemcpyAsync(grad, h->d_grad, nb, cudaMemcpyDeviceToHost, h->stream), "D2H grad");
+    CK(cudaStreamSynchronize(h->stream), "stream sync");
+    return MAGI_OK;
+}
+
+extern "C" int magi_logdensity_and_gradient(magi_handle* h, const double* params, int n_params, double* ll, double* grad) {
+    if (!h || !ll) return set_error(MAGI_ERR_INVALID_ARGUMENT, "logdensity_and_gradient: null argument");
+    if (n_params != h->P || !params) {          // interface.jl:179-182
+        *ll = -std::numeric_limits<double>::infinity();
+        if (grad) for (int i = 0; i < h->P; ++i) grad[i] = std::numeric_limits<double>::quiet_NaN();
+        g_last_error = "Dimension mismatch in logdensity_and_gradient";
+        return MAGI_OK;
+    }
+    return magi_logdensity_and_gradient_batched(h, 1, params, ll, grad);
+}
+
+extern "C" int magi_logdensity(magi_handle* h, const double* params, int n_params, double* ll) {
+    if (!h || !ll) return set_error(MAGI_ERR_INVALID_ARGUMENT, "logdensity: null argument");
+    if (n_params != h->P || !params) {          // interface.jl:113-116
+        *ll = -std::numeric_limits<double>::infinity();
+        g_last_error = "Dimension mismatch in logdensity";
+        return MAGI_OK;
+    }
+    // the reference computes the gradient and discards it (interface.jl:148); the kernel skips the stores
+    return magi_logdensity_and_gradient_batched(h, 1, params, ll, nullptr);
+}
+
+extern "C" int magi_set_band_tables(magi_handle* h, int dim, int which, const double* in) {
+    if (!h || !in) return set_error(MAGI_ERR_INVALID_ARGUMENT, "set_band_tables: null argument");
+    if (dim < 0 || dim >= h->D) return set_error(MAGI_ERR_INVALID_ARGUMENT, "set_band_tables: dim out of range");
+    if (which < MAGI_MAT_CINV_BAND || which > MAGI_MAT_KINV_BAND) return set_error(MAGI_ERR_INVALID_ARGUMENT, "set_band_tables: which must be a *_BAND selector");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    const size_t tab = (size_t)(2 * h->b + 1) * h->n;
+    const int t = which - MAGI_MAT_CINV_BAND;
+    CK(cudaMemcpy(h->d_band[t] + (size_t)dim * tab, in, sizeof(double) * tab, cudaMemcpyHostToDevice), "H2D band table");
+    h->band_set[(size_t)t * h->D + dim] = 1;
+    h->frag_dirty = true;
+    h->dense_band_dirty = true;
+    bool all = true;
+    for (char c : h->band_set) all = all && c;
+    if (all) h->tables_ready = true;
+    return MAGI_OK;
+}
+
+extern "C" int magi_get_matrix(magi_handle* h, int dim, int which, double* out) {
+    if (!h || !out) return set_error(MAGI_ERR_INVALID_ARGUMENT, "get_matrix: null argument");
+    if (dim < 0 || dim >= h->D) return set_error(MAGI_ERR_INVALID_ARGUMENT, "get_matrix: dim out of range");
+    CK(cudaSetDevice(h->device), "cudaSetDevice");
+    if (which >= MAGI_MAT_CINV_BAND && which <= MAGI_MAT_KINV_BAND) {
+        const size_t tab = (size_t)(2 * h->b + 1) * h->n;
+        CK(cudaMemcpy(out, h->d_band[which - MAGI_MAT_CINV_BAND] + (size_t)dim * tab, sizeof(double) * tab, cudaMemcpyDeviceToHost), "D2H band table");
+        return MAGI_OK;
+    }
+    if (which < 0 || which > MAGI_MAT_KINV) return set_error(MAGI_ERR_INVALID_ARGUMENT, "get_matrix: unknown selector");
+    if (!h->d_dense[which]) return set_error(MAGI_ERR_NOT_READY, "get_matrix: dense matrices exist only after a device setup (setup_mode != INJECT)");
+    const size_t nn = (size_t)h->n * h->n;
+    CK(cudaMemcpy(out, h->d_dense[which] + (size_t)dim * nn, sizeof(double) * nn, cudaMemcpyDeviceToHost), "D2H dense matrix");
+    return MAGI_OK;
+}
+
+extern "C" int magi_setup_status(magi_handle* h, int dim, int* rc_, int* rk_) {
+    if (!h || dim < 0 || dim >= h->D) return set_error(MAGI_ERR_INVALID_ARGUMENT, "setup_status: bad argument");
+    if (rc_) *rc_ = h->repaired_c[dim];
+    if (rk_) *rk_ = h->repaired_k[dim];
+    return MAGI_OK;
+}

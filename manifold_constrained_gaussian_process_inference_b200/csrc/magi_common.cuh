@@ -1,0 +1,61 @@
+// Shared declarations for libmagi_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/magi_b200.h"
+
+namespace magi {
+
+// ---- FP64 tensor-core primitive.  On sm_100a every f64 mma.sync shape lowers to SASS DMMA.8x8x4, which issues
+// once per 16 clk per SM sub-partition = 64 FMA/clk/SM, the full FP64 rate (measured 37.1 TFLOP/s,
+// profiles/fp64_peaks_r01.json).  Fragment layout, lane = 4*gid + q:
+//   A (8x4, row):  lane holds A[gid][q]        B (4x8, col): lane holds B[q][gid]
+//   C/D (8x8):     lane holds C[gid][2q], C[gid][2q+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// geometry of the banded DMMA tiling (see DESIGN.md "K1"): times are tiled by 8 (one DMMA N extent) and the
+// contraction runs over 4-time chunks; HB = ceil(b/4) chunks of half band on each side.
+struct BandGeom {
+    int n, b, HB, NCH, LAGT, WN, NT;
+};
+inline BandGeom band_geom(int n, int b) {
+    BandGeom g;
+    g.n = n; g.b = b;
+    g.HB = (b + 3) / 4;
+    g.NCH = 2 * g.HB + 2;
+    g.LAGT = (g.HB + 1) / 2;
+    g.WN = 2 * g.LAGT + 2 + g.HB;
+    g.NT = (n + 7) / 8;
+    return g;
+}
+constexpr int kMaxHB = 8;   // band half-widths up to 32 run on the windowed DMMA kernel
+
+struct BandedArgs {
+    int n, D, K, P, n_chains, NT, G, sigma_is_fixed, sigma_invalid, scratch_in_smem;
+    long long pitch;
+    const double* params;
+    double* ll;
+    double* grad;               // may be null (value only)
+    const double* fragtab;      // [4 views][D][NT][NCH][32]
+    const double* yobs;         // [D][n], non-finite = missing
+    const int* nobs;            // [D]
+    const double* sigma_init;   // [D]
+    double beta[3];
+    double inv_beta[3];
+    double* scratch;            // global Ke scratch when it does not fit shared memory
+};
+
+// launches (defined in the .cu files)
+cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
+                                 int n, int b, int D, cudaStream_t st);
+size_t banded_scratch_doubles_per_cta(int G, int D, int NT);
+void banded_pick_config(int model_D, int model_K, int NT, int smem_limit, int& G, int& DW, int& scratch_in_smem, size_t& smem_bytes);
+bool model_dims(int model, int& D, int& K);
+
+}  // namespace magi

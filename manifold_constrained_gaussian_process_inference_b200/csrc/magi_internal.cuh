@@ -1,0 +1,50 @@
+// Internal handle layout and cross-file entry points of libmagi_b200.so.
+#pragma once
+#include "magi_common.cuh"
+
+struct magi_handle {
+    int n = 0, D = 0, K = 0, P = 0, b = 0;
+    int kernel_id = 0, model = 0, sigma_is_fixed = 0, sigma_invalid = 0, setup_mode = 0, device = 0;
+    double jitter = 1e-6;
+    double beta[3] = {1.0, 1.0, 1.0};
+    std::vector<double> tvec, phi, yobs, sigma_init;
+    magi::BandGeom geom{};
+    // device-resident GP tables.  d_band[0..2] = CinvBand, mphiBand, KinvBand, each D x (2b+1) x n diagonal-major
+    double* d_band[3] = {nullptr, nullptr, nullptr};
+    // dense GPCov fields (C, Cinv, Cprime, Cdoubleprime, mphi, Kphi, Kinv), each D x n x n column-major; only after a device setup
+    double* d_dense[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* d_fragtab = nullptr;
+    double* d_yobs = nullptr;
+    int* d_nobs = nullptr;
+    double* d_sigma_init = nullptr;
+    std::vector<char> band_set;
+    bool tables_ready = false, frag_dirty = true, dense_band_dirty = true;
+    bool dense_mode = false;
+    // host-API staging
+    double *d_params = nullptr, *d_ll = nullptr, *d_grad = nullptr;
+    size_t cap_chains = 0;
+    double* d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    // dense-mode work space
+    double* d_dense_work = nullptr;
+    size_t dense_work_cap = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    int smem_limit = 0, sm_count = 148;
+    int G = 4, DW = 1, scratch_in_smem = 1;
+    size_t smem_bytes = 0;
+    std::vector<int> repaired_c, repaired_k;
+    void* hmc = nullptr;     // on-device sampler state (hmc.cu)
+};
+
+namespace magi {
+int set_error(int code, const std::string& msg);
+int cuda_error(cudaError_t e, const char* what);
+int ensure_capacity(magi_handle* h, int n_chains);
+int refresh_fragtab(magi_handle* h, cudaStream_t st);
+int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
+int eval_dense_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
+int run_device_setup(magi_handle* h);
+void hmc_free(magi_handle* h);
+cudaError_t launch_banded_cfg(int model, const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st);
+}  // namespace magi

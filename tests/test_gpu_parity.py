@@ -1,0 +1,133 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on identical inputs including the band tables.
+Tolerance: 1e-10 relative (north_star), written in tests/helpers.py."""
+import numpy as np
+import pytest
+
+from oracle import magi_oracle as mo
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_fn_case(missing=False):
+    """test/test_likelihoods.jl:18-59 (FN, N=3, RBF σ²=1.5 ℓ=1.2, b=1, ε=1e-5)."""
+    t = np.array([0.0, 1.0, 2.0])
+    covs = [mo.calculate_gp_covariances(mo.RBF, [1.5, 1.2], t, 1, complexity=2, jitter=1e-5) for _ in range(2)]
+    X = np.array([[1.0, 0.5], [1.1, 0.6], [1.2, 0.7]])
+    Y = X + np.array([[0.05, -0.02], [-0.01, 0.03], [0.02, 0.01]])
+    if missing:
+        Y[1, 0] = np.nan
+    sig = np.array([0.1, 0.15])
+    tgt = mo.make_target(Y, covs, mo.MODEL_FN, sig, (1.0, 1.0, 1.0), True)
+    params = np.concatenate([X.reshape(-1, order="F"), [0.5, 0.6, 0.7]])[None, :]
+    return dict(target=tgt, params=params, covs=covs)
+
+
+def test_reference_fn_case_fixed_sigma(pkg):
+    prob = _ref_fn_case()
+    tg = H.cuda_target(pkg, prob)
+    ll, g = tg.logdensity_and_gradient(prob["params"][0])
+    ll_ref, g_ref = mo.logdensity_and_gradient(prob["target"], prob["params"][0])
+    H.assert_parity([ll], g, [ll_ref], g_ref, "FN N=3")
+    assert abs(ll - (-1898.99907936565)) < 1e-6          # restated value, cross-checked in SURVEY.md section 8(c)
+    assert tg.dimension() == 9 and tg.capabilities() == pkg.LogDensityOrder(1)
+    assert abs(tg.logdensity(prob["params"][0]) - ll) <= 1e-12 * abs(ll)
+
+
+def test_reference_missing_observation_known_answer(pkg):
+    """test/test_likelihoods.jl:106-148: gradient element of the missing observation moves by exactly +1.0."""
+    full, miss = _ref_fn_case(False), _ref_fn_case(True)
+    ll_f, g_f = H.cuda_target(pkg, full).logdensity_and_gradient(full["params"][0])
+    ll_m, g_m = H.cuda_target(pkg, miss).logdensity_and_gradient(miss["params"][0])
+    assert ll_m < ll_f
+    assert abs((g_m[1] - g_f[1]) - 1.0) < 1e-6
+    others = np.delete(np.arange(9), 1)
+    assert np.max(np.abs(g_m[others] - g_f[others])) < 1e-6
+
+
+def test_reference_hes1_case(pkg):
+    """test/test_likelihoods.jl:165-179 (Hes1, D=3, k=7)."""
+    t = np.array([0.0, 1.0, 2.0])
+    covs = [mo.calculate_gp_covariances(mo.RBF, [1.5, 1.2], t, 1, complexity=2, jitter=1e-5) for _ in range(3)]
+    X = np.array([[1.0, 2.0, 3.0], [1.1, 2.1, 2.9], [1.2, 2.2, 2.8]])
+    Y = X + np.array([[0.01, 0.02, 0.03], [-0.02, -0.01, -0.03], [0.03, 0.01, 0.02]])
+    tgt = mo.make_target(Y, covs, mo.MODEL_HES1, [0.1, 0.2, 0.3], (1.0, 1.0, 1.0), False)
+    params = np.concatenate([X.reshape(-1, order="F"), [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7], np.log([0.1, 0.2, 0.3])])
+    prob = dict(target=tgt, params=params[None, :], covs=covs)
+    ll, g = H.cuda_target(pkg, prob).logdensity_and_gradient(params)
+    ll_ref, g_ref = mo.logdensity_and_gradient(tgt, params)
+    H.assert_parity([ll], g, [ll_ref], g_ref, "Hes1 N=3")
+
+
+@pytest.mark.parametrize("model,n,b,nc,kw", [
+    ("fn", 41, 6, 37, {}),
+    ("fn", 41, 40, 9, {}),                                  # full band == dense (test/test_gp.jl:551-585)
+    ("fn", 201, 20, 40, {}),                                # BASELINE config 2 shape
+    ("fn", 201, 20, 11, {"beta": (2.0, 3.0, 5.0)}),
+    ("fn", 397, 20, 8, {"beta": (1.0, 1.0, 5.0), "obs_every": 4, "T": 20.0}),   # BASELINE config 1 shape
+    ("fn", 16, 0, 8, {}),
+    ("fn", 9, 1, 3, {"kernel": mo.RBF}),
+    ("fn", 1, 0, 2, {"obs_every": 1}),
+    ("fn", 50, 16, 12, {"sigma_fixed": True}),
+    ("fn", 64, 32, 16, {}),
+    ("lv", 81, 20, 10, {"T": 4.0}),
+    ("hes1", 33, 5, 13, {}),
+])
+def test_batched_parity_random(pkg, model, n, b, nc, kw):
+    prob = H.make_problem(model=model, n=n, b=b, n_chains=nc, seed=n + b, **kw)
+    tg = H.cuda_target(pkg, prob)
+    ll, g = tg.logdensity_and_gradient_batched(prob["params"])
+    ll_ref, g_ref = H.oracle_batched(prob)
+    H.assert_parity(ll, g, ll_ref, g_ref, "%s n=%d b=%d" % (model, n, b))
+    # value-only variant and batched == single-chain
+    ll2, _ = tg.logdensity_and_gradient_batched(prob["params"], want_grad=False)
+    assert np.array_equal(ll, ll2)
+    l1, g1 = tg.logdensity_and_gradient(prob["params"][nc // 2])
+    assert l1 == ll[nc // 2] and np.array_equal(g1, g[nc // 2])
+
+
+def test_guards_per_chain(pkg):
+    """interface.jl:179-182, 222-226: wrong length -> (-Inf, NaN...); a non-finite chain -> (-Inf, 0...) without
+    poisoning its neighbours."""
+    prob = H.make_problem(n=41, b=6, n_chains=10, seed=5)
+    tg = H.cuda_target(pkg, prob)
+    params = prob["params"].copy()
+    params[3, 7] = np.nan
+    params[6, -1] = np.inf            # log sigma = +Inf -> clamped to 15 (finite result)
+    params[8, 41 * 2] = 0.0           # theta_a = 0 is fine; theta_c = 0 -> division by zero
+    params[8, 41 * 2 + 2] = 0.0
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    ll_ref, g_ref = H.oracle_batched(prob, params)
+    assert ll[3] == -np.inf and np.all(g[3] == 0.0)
+    assert ll[8] == -np.inf and np.all(g[8] == 0.0)
+    H.assert_parity(ll, g, ll_ref, g_ref, "guards")
+    l, gg = tg.logdensity_and_gradient(params[0][:-1])
+    assert l == -np.inf and np.all(np.isnan(gg)) and gg.shape[0] == tg.dimension()
+    assert tg.logdensity(params[0][:-1]) == -np.inf
+
+
+def test_extreme_theta_and_sparse_obs(pkg):
+    """test/test_likelihoods.jl:181-205."""
+    prob = _ref_fn_case()
+    p = prob["params"][0].copy()
+    p[6:9] = [1e-8, 1e8, 1.0]
+    ll, g = H.cuda_target(pkg, prob).logdensity_and_gradient(p)
+    ll_ref, g_ref = mo.logdensity_and_gradient(prob["target"], p)
+    assert np.isfinite(ll) and np.all(np.isfinite(g))
+    H.assert_parity([ll], g, [ll_ref], g_ref, "extreme theta")
+    Y = np.full((3, 2), np.nan)
+    Y[0, 0] = prob["target"].yobs[0, 0]
+    Y[2, 1] = prob["target"].yobs[2, 1]
+    prob["target"].yobs = Y
+    ll, g = H.cuda_target(pkg, prob).logdensity_and_gradient(prob["params"][0])
+    ll_ref, g_ref = mo.logdensity_and_gradient(prob["target"], prob["params"][0])
+    H.assert_parity([ll], g, [ll_ref], g_ref, "sparse obs")
+
+
+def test_tempering_changes_result(pkg):
+    """test/test_likelihoods.jl:158-163."""
+    p0 = H.make_problem(n=21, b=4, n_chains=2, seed=1)
+    p1 = H.make_problem(n=21, b=4, n_chains=2, seed=1, beta=(10.0, 1.0, 1.0))
+    l0, g0 = H.cuda_target(pkg, p0).logdensity_and_gradient_batched(p0["params"])
+    l1, g1 = H.cuda_target(pkg, p1).logdensity_and_gradient_batched(p1["params"])
+    assert np.all(l0 != l1) and not np.allclose(g0, g1, atol=1e-6, rtol=1e-6)
