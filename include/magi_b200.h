@@ -122,6 +122,14 @@ int magi_set_band_tables(magi_handle* h, int dim, int which, const double* in);
 /* status of the device setup for one dimension: repaired (non-positive) pivots seen in chol(C+eI), chol(K+eI) */
 int magi_setup_status(magi_handle* h, int dim, int* repaired_pivots_c, int* repaired_pivots_k);
 
+/* Stand-alone GPCov for ONE dimension, computed on the GPU: replaces calculate_gp_covariances!(gp_cov, kernel, phi, tvec,
+ * bandsize; complexity, jitter) (src/gaussian_process.jl:219-363).  phi = [variance, lengthscale]; outputs (any may be
+ * NULL): seven dense n x n column-major matrices and three (2b+1) x n band tables; repaired[2] = repaired pivot counts. */
+int magi_gp_covariances(int kernel_id, const double* phi, const double* tvec, int n, int bandsize, double jitter,
+                        int complexity, int setup_mode, int device, double* C, double* Cinv, double* Cprime,
+                        double* Cdoubleprime, double* mphi, double* Kphi, double* Kinv, double* CinvBand,
+                        double* mphiBand, double* KinvBand, int* repaired);
+
 /* introspection used by bench.py / tests: number of kernel launches issued by this handle so far */
 long long magi_launch_count(const magi_handle* h);
 

@@ -41,7 +41,7 @@ EXPORTED = [
     "magi_last_error", "magi_version", "magi_create", "magi_destroy", "magi_dimension", "magi_capabilities_order",
     "magi_logdensity", "magi_logdensity_and_gradient", "magi_logdensity_and_gradient_batched",
     "magi_logdensity_and_gradient_batched_dev", "magi_get_matrix", "magi_set_band_tables", "magi_setup_status",
-    "magi_launch_count",
+    "magi_launch_count", "magi_gp_covariances",
 ]
 
 

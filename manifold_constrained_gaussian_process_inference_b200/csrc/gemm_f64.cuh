@@ -1,0 +1,22 @@
+// Batched FP64 GEMM on DMMA.8x8x4 with generic element strides (any transpose / sub-matrix view), used by the GP
+// setup (blocked Cholesky trailing updates, triangular inverse, m = C'Cinv, K = C'' - m C'^T) and by the dense
+// (band = n-1) evaluation path.  C = alpha * A * B + beta * C, element A(i,k) = A[i*rsA + k*csA + z1*bsA1 + z2*bsA2].
+#pragma once
+#include "magi_common.cuh"
+
+namespace magi {
+
+struct GemmArgs {
+    const double* A; long long rsA, csA, bsA1, bsA2;
+    const double* B; long long rsB, csB, bsB1, bsB2;
+    double* C;       long long rsC, csC, bsC1, bsC2;
+    int M, N, K;
+    int nb1;              // inner batch count: blockIdx.z = z1 + nb1 * z2
+    double alpha, beta;
+    int lower_only;       // skip output tiles that lie strictly above the diagonal (symmetric updates)
+    int k_lo_from_tile;   // 1: A and B are lower-triangular-structured such that k < max(tile row0, tile col0) contributes 0
+};
+
+cudaError_t launch_gemm(const GemmArgs& g, int batch, cudaStream_t st);
+
+}  // namespace magi

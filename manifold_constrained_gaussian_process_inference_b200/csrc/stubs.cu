@@ -2,6 +2,5 @@
 #include "magi_internal.cuh"
 namespace magi {
 int eval_dense_dev(magi_handle*, int, const double*, long long, double*, double*, cudaStream_t) { return set_error(MAGI_ERR_UNSUPPORTED, "dense mode not built yet"); }
-int run_device_setup(magi_handle*) { return set_error(MAGI_ERR_UNSUPPORTED, "device setup not built yet"); }
 void hmc_free(magi_handle*) {}
 }

@@ -79,6 +79,55 @@ class MagiTarget:
                 T = np.ascontiguousarray(getattr(g, name), dtype=np.float64)
                 _lib.check(L.magi_set_band_tables(h, d, which, _lib.as_dp(T)))
 
+    @classmethod
+    def from_config(cls, yobs, tvec, phi_all_dims, ode_system: OdeSystem, sigma_init, prior_temperature=(1.0, 1.0, 1.0),
+                    sigma_is_fixed: bool = False, kernel: str = "matern52", bandsize: int = 20, jitter: float = 1e-6,
+                    setup_mode: str = "reference_order", device: int = 0, max_chains: int = 0) -> "MagiTarget":
+        """solve_magi's steps 4-5 in one call (src/MagiJl.jl:456-520): per-dimension GP setup from φ (2×D: row 0 variance,
+        row 1 lengthscale, :466-467) and target construction, all on the GPU (K3-K6 run inside ``magi_create``); nothing but
+        tvec, φ and yobs crosses PCIe.  bandsize is clamped to n−1 (:459)."""
+        L = _lib.lib()
+        self = cls.__new__(cls)
+        self.yobs = np.asfortranarray(np.asarray(yobs, dtype=np.float64))
+        n, D = self.yobs.shape
+        phi = np.asarray(phi_all_dims, dtype=np.float64)
+        if phi.shape != (2, D):
+            raise ValueError("phi_all_dims must be 2 x D")
+        self.gp_cov_all_dims = None
+        self.ode_system = ode_system
+        self.sigma_init = np.ascontiguousarray(sigma_init, dtype=np.float64)
+        self.prior_temperature = np.ascontiguousarray(prior_temperature, dtype=np.float64)
+        self.n_times, self.n_dims, self.n_params_ode = int(n), int(D), int(ode_system.thetaSize)
+        self.sigma_is_fixed = bool(sigma_is_fixed)
+        self.device = int(device)
+        self.bandsize = max(0, min(int(bandsize), n - 1))
+        tv = np.ascontiguousarray(tvec, dtype=np.float64)
+        phi_flat = np.ascontiguousarray(phi.T.reshape(-1))            # [var_0, len_0, var_1, len_1, ...]
+        cfg = _lib.MagiConfig(
+            n_times=n, n_dims=D, n_params_ode=self.n_params_ode, kernel_id={"matern52": _lib.KERNEL_MATERN52, "rbf": _lib.KERNEL_RBF}[kernel],
+            bandsize=int(bandsize), ode_model_id=ode_system.model_id, sigma_is_fixed=int(self.sigma_is_fixed),
+            setup_mode={"reference_order": _lib.SETUP_REFERENCE_ORDER, "stable": _lib.SETUP_STABLE}[setup_mode],
+            max_chains=int(max_chains), device=self.device, jitter=float(jitter), tvec=_lib.as_dp(tv), phi=_lib.as_dp(phi_flat),
+            yobs=_lib.as_dp(self.yobs.ravel(order="F")), sigma_init=_lib.as_dp(self.sigma_init),
+            prior_temperature=_lib.as_dp(self.prior_temperature))
+        h = ctypes.c_void_p()
+        _lib.check(L.magi_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h, self._L = h, L
+        return self
+
+    def get_matrix(self, dim: int, name: str) -> np.ndarray:
+        """Dense GPCov field of one dimension (only after a device setup): C, Cinv, Cprime, Cdoubleprime, mphi, Kphi, Kinv."""
+        which = {"C": _lib.MAT_C, "Cinv": _lib.MAT_CINV, "Cprime": _lib.MAT_CPRIME, "Cdoubleprime": _lib.MAT_CDOUBLEPRIME,
+                 "mphi": _lib.MAT_MPHI, "Kphi": _lib.MAT_KPHI, "Kinv": _lib.MAT_KINV}[name]
+        out = np.empty((self.n_times, self.n_times), order="F")
+        _lib.check(self._L.magi_get_matrix(self._h, dim, which, _lib.as_dp(out)))
+        return out
+
+    def setup_status(self, dim: int):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._L.magi_setup_status(self._h, dim, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
     # ---- LogDensityProblems interface ----
     def dimension(self) -> int:
         return int(self._L.magi_dimension(self._h))

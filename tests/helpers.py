@@ -13,6 +13,8 @@ GRAD_FLOOR = 1e-3         # individual elements carry ~1e-12 relative rounding f
 
 def fn_truth(tvec, theta=(0.2, 0.2, 3.0), x0=(-1.0, 1.0)):
     from scipy.integrate import solve_ivp
+    if len(tvec) == 1:
+        return np.array([x0], dtype=np.float64)
     a, b, c = theta
     f = lambda t, u: [c * (u[0] - u[0] ** 3 / 3 + u[1]), -(u[0] - a + b * u[1]) / c]
     sol = solve_ivp(f, (tvec[0], tvec[-1]), x0, t_eval=tvec, rtol=1e-8, atol=1e-10)
