@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- leapfrog gradient evaluations per second of the MAGI hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle C port, all host cores)
+
+One "step" = one logdensity_and_gradient pass over one batch of chains (BASELINE configs[1]: FitzHugh-Nagumo,
+n=201, band 20, 4096 chains per GPU).  Chains shard across ranks with no data-path collective (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "fp64_tflops": 37.1, "fp64_src": "profiles/fp64_peaks_r01.json"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        peaks["hbm_gbs"] = float(m["hbm_gbs"]); peaks["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")) as f:
+            m = json.load(f)
+        peaks["fp64_tflops"] = float(m["fp64_dmma_tflops"])
+        peaks["fp64_src"] = "measured FP64 DMMA.8x8x4 peak (profiles/fp64_peaks_r01.json; MEASURED_PEAKS.json has no FP64 figure)"
+    except Exception:
+        pass
+    return peaks
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+    def __init__(self, index):
+        self.samples, self.reasons, self.maxmhz, self._stop = [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxmhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and not nm.endswith("None") and not nm.endswith("All"):
+                        self.reasons.add(nm.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.maxmhz, "reasons": sorted(x for x in self.reasons if x not in ("GpuIdle",)),
+                "samples": len(s)}
+
+
+def cpu_arm(work, tables, steps, warmup, chains, nthreads=0, min_seconds=0.0):
+    """Times the oracle's C restatement of the reference path (all host threads) on the same inputs and band tables."""
+    from oracle import c_oracle, magi_oracle as mo
+    covs = []
+    for d in range(work["D"]):
+        g = mo.GPCov(bandsize=work["bandsize"], tvec=work["tvec"])
+        g.CinvBand, g.mphiBand, g.KinvBand = tables[d]
+        covs.append(g)
+    mid = {"fn": mo.MODEL_FN, "lv": mo.MODEL_LV}[work["model"]]
+    tgt = mo.make_target(work["yobs"], covs, mid, work["sigma_init"], work["beta"], False)
+    params = work["params"][:chains]
+    for _ in range(max(1, warmup)):
+        ll, g = c_oracle.batched(tgt, params, nthreads)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps or (time.perf_counter() - t0) < min_seconds:
+        ll, g = c_oracle.batched(tgt, params, nthreads)
+        done += 1
+    dt = time.perf_counter() - t0
+    return dict(evals_per_s=chains * done / dt, seconds=dt, passes=done, cores=(nthreads or c_oracle.num_threads()), ll=ll, grad=g)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fn201")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--bandsize", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import manifold_constrained_gaussian_process_inference_b200 as pkg
+    from manifold_constrained_gaussian_process_inference_b200 import synthetic
+
+    chains = args.chains or synthetic.CONFIGS[args.workload]["chains"]
+    work = synthetic.make_workload(args.workload, chains, rank=rank, bandsize=(args.bandsize if args.bandsize >= 0 else None))
+    n, D, k, b = work["n"], work["D"], work["k"], work["bandsize"]
+    P = n * D + k + D
+    config = {"workload": "%s: %s n=%d D=%d k=%d band=%d matern52 jitter=1e-6, %d chains/GPU, sigma sampled" % (args.workload, work["model"], n, D, k, b, chains),
+              "chains_per_gpu": chains, "n_times": n, "bandsize": b, "sharding": "chains across ranks, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # band tables for the CPU arm: built by the oracle itself (this arm runs none of our kernels)
+        from oracle import magi_oracle as mo
+        tables = []
+        for d in range(D):
+            g = mo.calculate_gp_covariances(mo.MATERN52, work["phi"][:, d], work["tvec"], b, jitter=1e-6, setup_mode="stable")
+            tables.append((g.CinvBand, g.mphiBand, g.KinvBand))
+        res = cpu_arm(work, tables, args.steps, warmup, chains)
+        val = res["evals_per_s"]
+        out = {"impl": "reference", "metric": "leapfrog grad evals/sec (all chains)", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+               "steps": res["passes"], "warmup": warmup, "ms_per_step": res["seconds"] / res["passes"] * 1e3, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": val, "unit": "evals/s", "cores": res["cores"], "kind": "port",
+                                "sample": "%d passes over the %d-chain batch, C restatement of likelihoods.jl + interface.jl, OpenMP over chains" % (res["passes"], chains)},
+               "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    tg = pkg.MagiTarget.from_config(work["yobs"], work["tvec"], work["phi"], pkg.get_ode_system(work["model"]), work["sigma_init"],
+                                    prior_temperature=work["beta"], sigma_is_fixed=False, kernel="matern52", bandsize=b, jitter=1e-6,
+                                    setup_mode="stable", device=local, max_chains=chains)
+    assert tg.dimension() == P
+    # rotating input/output sets so that consecutive steps never find their operands in the 126 MB L2
+    bytes_per_set = chains * (2 * P + 1) * 8
+    nsets = max(2, int(np.ceil(2.5 * 126e6 / bytes_per_set)))
+    host = torch.from_numpy(work["params"])
+    psets = [(host.to(dev) + (1e-6 * s)).contiguous() for s in range(nsets)]
+    gsets = [torch.empty_like(psets[0]) for _ in range(nsets)]
+    lsets = [torch.empty(chains, dtype=torch.float64, device=dev) for _ in range(nsets)]
+    config["l2"] = "rotating %d input/output sets (%.0f MB) > 126 MB L2, no explicit flush" % (nsets, nsets * bytes_per_set / 1e6)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        s = i % nsets
+        tg.logdensity_and_gradient_batched_dev(chains, psets[s].data_ptr(), lsets[s].data_ptr(), gsets[s].data_ptr(), stream)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = tg.launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = tg.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- e2e: the public host API (HOST buffers in, HOST buffers out; copies inside the timed region) ----
+    hp = torch.from_numpy(work["params"]).pin_memory()
+    hg = torch.empty_like(hp).pin_memory()
+    hl = torch.empty(chains, dtype=torch.float64).pin_memory()
+    hp_np, hg_np, hl_np = hp.numpy(), hg.numpy(), hl.numpy()
+    from manifold_constrained_gaussian_process_inference_b200 import _lib
+    L = _lib.lib()
+
+    def e2e_step():
+        _lib.check(L.magi_logdensity_and_gradient_batched(tg._h, chains, _lib.as_dp(hp_np), _lib.as_dp(hl_np), _lib.as_dp(hg_np)))
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * chains * args.steps / (ms * 1e-3)
+        per_launch_s = ms * 1e-3 / args.steps
+        flops = synthetic.algorithmic_flops_per_eval(n, D, b)
+        abytes = synthetic.algorithmic_bytes_per_eval(P)
+        tf = chains * flops / per_launch_s * 1e-12
+        gbs = chains * abytes / per_launch_s * 1e-9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("workload") == args.workload and tj.get("chains") == chains:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        out = {"metric": "leapfrog grad evals/sec (all chains)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+               "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": int(launches), "clocks": clocks,
+               "e2e": {"value": world * chains * e2e_steps / e2e_dt, "unit": "evals/s", "h2d_bytes_per_step": chains * P * 8,
+                       "d2h_bytes_per_step": chains * (P + 1) * 8, "steps": e2e_steps, "api": "magi_logdensity_and_gradient_batched (pinned host buffers)"},
+               "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_tflops"],
+                            "traffic": traffic, "kernel": "banded_logpost_kernel", "peak_source": peaks["fp64_src"],
+                            "algorithmic_flops_per_eval": flops,
+                            "note": "band 20 is FP64-pipe bound (AI %.1f flop/B vs ridge %.1f): the binding roof is the FP64 tensor (DMMA) pipe" % (flops / abytes, peaks["fp64_tflops"] * 1e3 / peaks["hbm_gbs"])},
+               "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                "algorithmic_bytes_per_eval": abytes, "peak_source": peaks["hbm_src"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            tables = [(tg.get_band_table(d, "CinvBand"), tg.get_band_table(d, "mphiBand"), tg.get_band_table(d, "KinvBand")) for d in range(D)]
+            res = cpu_arm(work, tables, 1, 1, chains, min_seconds=args.cpu_seconds)
+            out["cpu_baseline"] = {"value": res["evals_per_s"], "unit": "evals/s", "cores": res["cores"], "kind": "port",
+                                   "sample": "%d passes over the %d-chain batch in %.1f s (C restatement of the reference loop, OpenMP over chains, same band tables)" % (res["passes"], chains, res["seconds"])}
+            # parity spot check of the measured kernel against the CPU arm (not timed)
+            ll_gpu = lsets[0].cpu().numpy()
+            ll0, _ = tg.logdensity_and_gradient_batched(work["params"][:64])
+            out["parity_ll_max_rel_err_vs_cpu"] = float(np.max(np.abs(ll0 - res["ll"][:64]) / np.abs(res["ll"][:64])))
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
