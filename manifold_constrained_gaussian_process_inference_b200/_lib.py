@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmagi_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("MAGI_LIB_NAME", "libmagi_b200.so"))
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libmagi_b200.so")
+OBJDIR = os.path.join(HERE, os.environ.get("MAGI_OBJ_DIR", "build"))
+LIB = os.path.join(LIBDIR, os.environ.get("MAGI_LIB_NAME", "libmagi_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
@@ -44,7 +44,7 @@ def _compile(src, extra):
 def build(force: bool = False, fast: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    extra = {"force": force, "defs": ["-DMAGI_FAST_BUILD"] if fast else []}
+    extra = {"force": force, "defs": (["-DMAGI_FAST_BUILD"] if fast else []) + os.environ.get("MAGI_EXTRA_DEFS", "").split()}
     srcs = sources()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, extra), srcs))

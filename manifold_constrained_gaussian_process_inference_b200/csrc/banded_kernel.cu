@@ -19,6 +19,7 @@
 //   final   (per chain):  log-likelihood assembly in the reference's term order, sigma gradient, log-sigma
 //                         transform and the per-chain -Inf / zero-gradient guards.
 #include <cmath>
+#include <cstdlib>
 #include "magi_common.cuh"
 #include "ode_models.cuh"
 
@@ -75,24 +76,33 @@ __device__ __forceinline__ double quad_sum(double v) {
     return v;
 }
 
-// block = G chain-groups x DW(=D) dimension slots warps, at most 4*D (capped at 16) warps: the register budget
-// follows from the model's D (FN: 256 threads -> up to 255 registers per thread).
-template <int MODEL> constexpr int banded_max_threads() { return Ode<MODEL>::D * 128 > 512 ? 512 : Ode<MODEL>::D * 128; }
-
+// One block = G chain-groups (8 chains each) x DW dimension slots x H time segments, one warp per (group, dim, segment)
+// task.  Three barrier-separated phases; e and Ke live in a scratch area laid out in fragment order
+// scr[(g*D + d)*NT + tile][2][32] (shared memory when it fits, else global/L2), so that
+//   * the time axis splits across warps with no halo recomputation (a neighbour's e / Ke is read from the scratch),
+//   * the A operands of K~ e and m~^T Ke are plain conflict-free LDS, with no register window,
+//   * the register budget stays <= 128, i.e. 16 resident warps per SM (the kernel is latency-, not issue-bound).
+//   P1: e  = f_d(x, theta) - m~ x_d          (x_d in a sliding register window fed from global memory)
+//   P2: Ke = K~ e ;  sum e.Ke
+//   P3: Cx = C~ x_d ; mt = m~^T Ke_d ; pointwise gradient incl. the ODE Jacobian terms (need Ke of all dimensions)
 template <int MODEL, int HB>
-__global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost_kernel(const BandedArgs a) {
+__global__ void __launch_bounds__(256, 2) banded_logpost_kernel(const BandedArgs a) {
     using M = Ode<MODEL>;
     constexpr int D = M::D, K = M::K;
-    constexpr int NCH = 2 * HB + 2, LAGT = (HB + 1) / 2, WN = 2 * LAGT + 2 + HB;
+    constexpr int NCH = 2 * HB + 2, LAGT = (HB + 1) / 2, WN = 2 * LAGT + 2 + HB, CH2 = (HB + 1) / 2;
     constexpr int RED = 4 + K;   // e.Ke, x.Cx, sse, bad flag, theta-gradient partials
     extern __shared__ double smem[];
-    const int NT = a.NT, n = a.n, G = a.G;
+    const int NT = a.NT, n = a.n, G = a.G, H = a.H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
-    const int DW = (blockDim.x >> 5) / G;            // dimensions processed concurrently by the block
-    const int g = warp % G, dslot = warp / G;
+    const int nwarps = blockDim.x >> 5;
+    const int DW = nwarps / (G * H);                 // dimensions processed concurrently by the block
+    const int g = warp % G, dslot = (warp / G) % DW, h = warp / (G * DW);
+    const int TPS = (NT + H - 1) / H;
+    const int T0 = h * TPS, T1 = (T0 + TPS < NT) ? T0 + TPS : NT;
     const size_t scr_doubles = (size_t)G * D * NT * 64;
-    double* scr = a.scratch_in_smem ? smem : a.scratch + (size_t)blockIdx.x * scr_doubles;
-    double* red = smem + (a.scratch_in_smem ? scr_doubles : 0);          // [G*8][D][RED]
+    double* escr = a.scratch_in_smem ? smem : a.scratch + (size_t)blockIdx.x * 2 * scr_doubles;
+    double* kscr = escr + scr_doubles;
+    double* red = smem + (a.scratch_in_smem ? 2 * scr_doubles : 0);          // [G*8][D][H][RED]
 
     const long long chain = (long long)blockIdx.x * (G * 8) + g * 8 + gid;
     const bool cvalid = chain < a.n_chains;
@@ -101,32 +111,33 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
 #pragma unroll
     for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
     const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
+#ifdef MAGI_DBG_FINE
+    long long fine[4] = {0, 0, 0, 0};
+#endif
+    if (a.dbg) tk0 = clock64();
 
-    // ---------------- phase A1: mx, e, Ke ----------------
+    // ---------------- P1: e = f - m~ x ----------------
     for (int d = dslot; d < D; d += DW) {
-        double xw[WN], ew[WN];
+        double xw[WN];
 #pragma unroll
-        for (int i = 0; i < WN; ++i) { xw[i] = 0.0; ew[i] = 0.0; }
-        double acc_eke = 0.0;
+        for (int i = 0; i < WN; ++i) xw[i] = 0.0;
         const double* xd = xp + (size_t)d * n;
-        double* kscr = scr + ((size_t)(g * D + d) * NT) * 64 + lane;
+        double* es = escr + ((size_t)(g * D + d) * NT) * 64 + lane;
         const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NT) * NCH * 32 + lane;
-        const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NT) * NCH * 32 + lane;
-        for (int s = 0; s < NT + 2 * LAGT; ++s) {
+        const int s_begin = T0 - CH2, s_end = T1 - 1 + LAGT;
+        double nx0, nx1;
+        { const int t0 = 8 * s_begin + q, t1 = t0 + 4;
+          nx0 = (t0 >= 0 && t0 < n) ? xd[t0] : 0.0; nx1 = (t1 >= 0 && t1 < n) ? xd[t1] : 0.0; }
+        for (int s = s_begin; s <= s_end; ++s) {
 #pragma unroll
-            for (int i = 0; i < WN - 2; ++i) { xw[i] = xw[i + 2]; ew[i] = ew[i + 2]; }
-            {
-                const int t0 = 8 * s + q, t1 = t0 + 4;
-                xw[WN - 2] = (t0 < n) ? xd[t0] : 0.0;      // s >= NT implies t0 >= n
-                xw[WN - 1] = (t1 < n) ? xd[t1] : 0.0;
-            }
+            for (int i = 0; i < WN - 2; ++i) xw[i] = xw[i + 2];
+            xw[WN - 2] = nx0;
+            xw[WN - 1] = nx1;
+            { const int t0 = 8 * (s + 1) + q, t1 = t0 + 4;           // next step's window feed
+              nx0 = (t0 >= 0 && t0 < n) ? xd[t0] : 0.0; nx1 = (t1 >= 0 && t1 < n) ? xd[t1] : 0.0; }
             const int Ja = s - LAGT;
-            double e0 = 0.0, e1 = 0.0;
-            if (Ja >= 0 && Ja < NT) {
-                double m0 = 0.0, m1 = 0.0;
-                const double* f = ft0 + (size_t)Ja * NCH * 32;
-#pragma unroll
-                for (int hh = 0; hh < NCH; ++hh) dmma884(m0, m1, xw[hh], __ldg(f + hh * 32));
+            if (Ja >= T0) {                                           // Ja < T1 by the loop bound
                 const int t0 = 8 * Ja + q, t1 = t0 + 4;
                 double xa[D], xb[D];
 #pragma unroll
@@ -134,33 +145,61 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
                     xa[dd] = (t0 < n) ? xp[(size_t)dd * n + t0] : 0.0;
                     xb[dd] = (t1 < n) ? xp[(size_t)dd * n + t1] : 0.0;
                 }
-                if (t0 < n) e0 = M::f(d, xa, th) - m0;     // likelihoods.jl:130
-                if (t1 < n) e1 = M::f(d, xb, th) - m1;
-            }
-            ew[WN - 2] = e0;
-            ew[WN - 1] = e1;
-            const int Jb = s - 2 * LAGT;
-            if (Jb >= 0 && Jb < NT) {
-                double k0 = 0.0, k1 = 0.0;
-                const double* f = ft2 + (size_t)Jb * NCH * 32;
+                const double* f = ft0 + (size_t)Ja * NCH * 32;
+                double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
 #pragma unroll
-                for (int hh = 0; hh < NCH; ++hh) dmma884(k0, k1, ew[hh], __ldg(f + hh * 32));
-                kscr[(size_t)Jb * 64] = k0;                // likelihoods.jl:132
-                kscr[(size_t)Jb * 64 + 32] = k1;
-                acc_eke += ew[HB] * k0;                     // likelihoods.jl:146
-                acc_eke += ew[HB + 1] * k1;
+                for (int hh = 0; hh < NCH; hh += 2) {
+                    dmma884(m0, m1, xw[hh], __ldg(f + hh * 32));
+                    dmma884(m2, m3, xw[hh + 1], __ldg(f + (hh + 1) * 32));
+                }
+                m0 += m2; m1 += m3;                                   // likelihoods.jl:129
+                double e0 = 0.0, e1 = 0.0;
+                if (t0 < n) e0 = M::f(d, xa, th) - m0;                // likelihoods.jl:130
+                if (t1 < n) e1 = M::f(d, xb, th) - m1;
+                es[(size_t)Ja * 64] = e0;
+                es[(size_t)Ja * 64 + 32] = e1;
             }
         }
-        acc_eke = quad_sum(acc_eke);
-        if (q == 0) red[((size_t)(g * 8 + gid) * D + d) * RED + 0] = acc_eke;
     }
+    if (a.dbg) tk1 = clock64();
     __syncthreads();
+    if (a.dbg) tk2 = clock64();
 
-    // ---------------- phase A2: Cx, m^T Ke, pointwise gradient ----------------
+    // ---------------- P2: Ke = K~ e ----------------
     for (int d = dslot; d < D; d += DW) {
-        double xw[WN], kw[WN];
+        const double* es = escr + ((size_t)(g * D + d) * NT) * 64 + lane;
+        double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
+        const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NT) * NCH * 32 + lane;
+        double acc_eke = 0.0;
+        for (int J = T0; J < T1; ++J) {
+            const double* f = ft2 + (size_t)J * NCH * 32;
+            double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;
 #pragma unroll
-        for (int i = 0; i < WN; ++i) { xw[i] = 0.0; kw[i] = 0.0; }
+            for (int hh = 0; hh < NCH; hh += 2) {
+                const int c0 = 2 * J - HB + hh, c1 = c0 + 1;          // operand chunks (4 times each)
+                const double o0 = (c0 >= 0 && c0 < 2 * NT) ? es[(size_t)(c0 >> 1) * 64 + (c0 & 1) * 32] : 0.0;
+                const double o1 = (c1 >= 0 && c1 < 2 * NT) ? es[(size_t)(c1 >> 1) * 64 + (c1 & 1) * 32] : 0.0;
+                dmma884(k0, k1, o0, __ldg(f + hh * 32));
+                dmma884(k2, k3, o1, __ldg(f + (hh + 1) * 32));
+            }
+            k0 += k2; k1 += k3;                                       // likelihoods.jl:132
+            ks[(size_t)J * 64] = k0;
+            ks[(size_t)J * 64 + 32] = k1;
+            acc_eke += es[(size_t)J * 64] * k0;                        // likelihoods.jl:146
+            acc_eke += es[(size_t)J * 64 + 32] * k1;
+        }
+        acc_eke = quad_sum(acc_eke);
+        if (q == 0) red[(((size_t)(g * 8 + gid) * D + d) * H + h) * RED + 0] = acc_eke;
+    }
+    if (a.dbg) tk3 = clock64();
+    __syncthreads();
+    if (a.dbg) tk4 = clock64();
+
+    // ---------------- P3: Cx, m^T Ke, pointwise gradient ----------------
+    for (int d = dslot; d < D; d += DW) {
+        double xw[WN];
+#pragma unroll
+        for (int i = 0; i < WN; ++i) xw[i] = 0.0;
         double acc_xcx = 0.0, acc_sse = 0.0;
         double gth[K];
 #pragma unroll
@@ -169,65 +208,89 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
         double sigma_d;
         if (a.sigma_is_fixed) sigma_d = a.sigma_init[d];
         else {
-            double ls = xp[(size_t)n * D + K + d];
-            ls = fmin(fmax(ls, -15.0), 15.0);               // interface.jl:200 (NaN propagates through exp below)
-            sigma_d = isnan(xp[(size_t)n * D + K + d]) ? xp[(size_t)n * D + K + d] : exp(ls);
+            const double raw = xp[(size_t)n * D + K + d];
+            const double ls = fmin(fmax(raw, -15.0), 15.0);           // interface.jl:200
+            sigma_d = isnan(raw) ? raw : exp(ls);
         }
         const double inv_sig2 = 1.0 / (sigma_d * sigma_d);
         const double* xd = xp + (size_t)d * n;
         const double* yd = a.yobs + (size_t)d * n;
-        const double* kscr = scr + ((size_t)(g * D + d) * NT) * 64 + lane;
+        const double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
         const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NT) * NCH * 32 + lane;
         const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NT) * NCH * 32 + lane;
         double* gout = (a.grad != nullptr && cvalid) ? a.grad + chain * a.pitch + (size_t)d * n : nullptr;
-        for (int s = 0; s < NT + LAGT; ++s) {
+        const int s_begin = T0 - CH2, s_end = T1 - 1 + LAGT;
+        double nx0, nx1;
+        { const int t0 = 8 * s_begin + q, t1 = t0 + 4;
+          nx0 = (t0 >= 0 && t0 < n) ? xd[t0] : 0.0; nx1 = (t1 >= 0 && t1 < n) ? xd[t1] : 0.0; }
+        for (int s = s_begin; s <= s_end; ++s) {
 #pragma unroll
-            for (int i = 0; i < WN - 2; ++i) { xw[i] = xw[i + 2]; kw[i] = kw[i + 2]; }
-            {
-                const int t0 = 8 * s + q, t1 = t0 + 4;
-                xw[WN - 2] = (t0 < n) ? xd[t0] : 0.0;
-                xw[WN - 1] = (t1 < n) ? xd[t1] : 0.0;
-                kw[WN - 2] = (s < NT) ? kscr[(size_t)s * 64] : 0.0;
-                kw[WN - 1] = (s < NT) ? kscr[(size_t)s * 64 + 32] : 0.0;
-            }
+            for (int i = 0; i < WN - 2; ++i) xw[i] = xw[i + 2];
+            xw[WN - 2] = nx0;
+            xw[WN - 1] = nx1;
+            { const int t0 = 8 * (s + 1) + q, t1 = t0 + 4;
+              nx0 = (t0 >= 0 && t0 < n) ? xd[t0] : 0.0; nx1 = (t1 >= 0 && t1 < n) ? xd[t1] : 0.0; }
             const int Jc = s - LAGT;
-            if (Jc >= 0 && Jc < NT) {
-                double c0 = 0.0, c1 = 0.0, u0 = 0.0, u1 = 0.0;
+            if (Jc >= T0) {
+#ifdef MAGI_DBG_FINE
+                const long long f0 = clock64();
+#endif
+                const int t0 = 8 * Jc + q, t1 = t0 + 4;
+                double xa[D], xb[D], wa[D], wb[D];
+#pragma unroll
+                for (int dd = 0; dd < D; ++dd) {
+                    xa[dd] = (t0 < n) ? xp[(size_t)dd * n + t0] : 0.0;
+                    xb[dd] = (t1 < n) ? xp[(size_t)dd * n + t1] : 0.0;
+                    const double* wsrc = kscr + ((size_t)(g * D + dd) * NT + Jc) * 64 + lane;
+                    wa[dd] = wsrc[0] * inv_b1;                         // likelihoods.jl:201
+                    wb[dd] = wsrc[32] * inv_b1;
+                }
+                const double y0 = (t0 < n) ? __ldg(yd + t0) : 0.0, y1 = (t1 < n) ? __ldg(yd + t1) : 0.0;
                 const double* f1 = ft1 + (size_t)Jc * NCH * 32;
                 const double* f3 = ft3 + (size_t)Jc * NCH * 32;
+                double c0 = 0.0, c1 = 0.0, u0 = 0.0, u1 = 0.0;
+#ifdef MAGI_DBG_FINE
+                const long long f1c = clock64();
+#endif
 #pragma unroll
                 for (int hh = 0; hh < NCH; ++hh) {
-                    dmma884(c0, c1, xw[hh], __ldg(f1 + hh * 32));     // likelihoods.jl:133
-                    dmma884(u0, u1, kw[hh], __ldg(f3 + hh * 32));     // likelihoods.jl:192
+                    const int ck = 2 * Jc - HB + hh;
+                    const double ko = (ck >= 0 && ck < 2 * NT) ? ks[(size_t)(ck >> 1) * 64 + (ck & 1) * 32] : 0.0;
+                    dmma884(c0, c1, xw[hh], __ldg(f1 + hh * 32));       // likelihoods.jl:133
+                    dmma884(u0, u1, ko, __ldg(f3 + hh * 32));           // likelihoods.jl:192
                 }
+#ifdef MAGI_DBG_FINE
+                const long long f2c = clock64() + (long long)(c0 * 0.0) + (long long)(u0 * 0.0);
+#endif
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int t = 8 * Jc + q + 4 * u;
+                    const int t = u ? t1 : t0;
                     if (t < n) {
                         const double cx = u ? c1 : c0, mt = u ? u1 : u0;
-                        double xa[D], w[D];
+                        const double* xv = u ? xb : xa;
+                        const double* w = u ? wb : wa;
                         double xdv = 0.0, wd = 0.0;
 #pragma unroll
-                        for (int dd = 0; dd < D; ++dd) {
-                            xa[dd] = xp[(size_t)dd * n + t];
-                            w[dd] = scr[((size_t)(g * D + dd) * NT + Jc) * 64 + u * 32 + lane] * inv_b1;   // likelihoods.jl:201
-                            if (dd == d) { xdv = xa[dd]; wd = w[dd]; }
-                        }
-                        const double y = yd[t];
+                        for (int dd = 0; dd < D; ++dd) if (dd == d) { xdv = xv[dd]; wd = w[dd]; }
+                        const double y = u ? y1 : y0;
                         const bool fin = isfinite(y);                  // likelihoods.jl:123
                         const double e0 = fin ? xdv - y : 0.0;
                         double gv = 0.0;
                         if (fin) gv -= (e0 * inv_sig2) * inv_b3;       // likelihoods.jl:179
                         gv -= cx * inv_b2;                             // likelihoods.jl:186
                         gv += mt * inv_b1;                             // likelihoods.jl:194
-                        M::jx_col_sub(d, xa, th, w, gv);               // likelihoods.jl:214-216
-                        M::jth_row_sub(d, xa, th, wd, gth);            // likelihoods.jl:219-221
+                        M::jx_col_sub(d, xv, th, w, gv);               // likelihoods.jl:214-216
+                        M::jth_row_sub(d, xv, th, wd, gth);            // likelihoods.jl:219-221
                         acc_xcx += xdv * cx;                           // likelihoods.jl:150
                         acc_sse += e0 * e0;                            // likelihoods.jl:139,234
                         bad |= !isfinite(gv);
                         if (gout != nullptr) gout[t] = gv;
                     }
                 }
+#ifdef MAGI_DBG_FINE
+                const long long f3c = clock64() + (long long)(acc_xcx * 0.0);
+                fine[0] += f1c - f0; fine[1] += f2c - f1c; fine[2] += f3c - f2c; fine[3] += 1;
+#endif
             }
         }
         acc_xcx = quad_sum(acc_xcx);
@@ -236,7 +299,7 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
         for (int i = 0; i < K; ++i) gth[i] = quad_sum(gth[i]);
         const unsigned badm = __ballot_sync(0xffffffffu, bad);
         if (q == 0) {
-            double* r = red + ((size_t)(g * 8 + gid) * D + d) * RED;
+            double* r = red + (((size_t)(g * 8 + gid) * D + d) * H + h) * RED;
             r[1] = acc_xcx;
             r[2] = acc_sse;
             r[3] = ((badm >> (gid * 4)) & 0xfu) ? 1.0 : 0.0;
@@ -244,7 +307,15 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
             for (int i = 0; i < K; ++i) r[4 + i] = gth[i];
         }
     }
+    if (a.dbg) tk5 = clock64();
     __syncthreads();
+    if (a.dbg && lane == 0) {
+        long long* o = a.dbg + ((size_t)blockIdx.x * nwarps + warp) * 8;
+        o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tk3 - tk2; o[3] = tk4 - tk3; o[4] = tk5 - tk4; o[5] = clock64() - tk5;
+#ifdef MAGI_DBG_FINE
+        o[5] = fine[0]; o[6] = fine[1]; o[7] = fine[2];
+#endif
+    }
 
     // ---------------- final: one thread per chain ----------------
     if (threadIdx.x < G * 8) {
@@ -266,7 +337,14 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
             for (int i = 0; i < K; ++i) gthf[i] = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const double* r = red + ((size_t)threadIdx.x * D + d) * RED;
+                double eke = 0.0, xcx = 0.0, sse = 0.0;
+                for (int hh = 0; hh < H; ++hh) {
+                    const double* r = red + (((size_t)threadIdx.x * D + d) * H + hh) * RED;
+                    eke += r[0]; xcx += r[1]; sse += r[2];
+                    bad |= (r[3] != 0.0);
+#pragma unroll
+                    for (int i = 0; i < K; ++i) gthf[i] += r[4 + i];
+                }
                 double s;
                 if (a.sigma_is_fixed) s = a.sigma_init[d];
                 else {
@@ -278,15 +356,13 @@ __global__ void __launch_bounds__(banded_max_threads<MODEL>(), 1) banded_logpost
                 sig[d] = s;
                 const double s2 = s * s;
                 const int nobs = a.nobs[d];
-                double ll_obs = -0.5 * r[2] / s2;                     // likelihoods.jl:139
+                double ll_obs = -0.5 * sse / s2;                      // likelihoods.jl:139
                 if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);   // :141
                 ll += ll_obs / a.beta[2];                             // :143
-                ll += (-0.5 * r[0]) / a.beta[0];                      // :146-147
-                ll += (-0.5 * r[1]) / a.beta[1];                      // :150-151
-                gsig[d] = (s > 0 && nobs > 0) ? (r[2] / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
-                bad |= (r[3] != 0.0) | !isfinite(gsig[d]);
-#pragma unroll
-                for (int i = 0; i < K; ++i) gthf[i] += r[4 + i];
+                ll += (-0.5 * eke) / a.beta[0];                       // :146-147
+                ll += (-0.5 * xcx) / a.beta[1];                       // :150-151
+                gsig[d] = (s > 0 && nobs > 0) ? (sse / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
+                bad |= !isfinite(gsig[d]);
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) bad |= !isfinite(gthf[i]);
@@ -337,23 +413,35 @@ bool model_dims(int model, int& D, int& K) {
     }
 }
 
-size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)G * D * NT * 64; }
+size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)2 * G * D * NT * 64; }   // e and Ke
 
-// Chooses chain-groups per block (G), concurrently processed dimensions (DW) and where the Ke scratch lives.
-void banded_pick_config(int D, int K, int NT, int smem_limit, int& G, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
+// Chooses chain-groups per block (G), time segments (H), concurrently processed dimensions (DW) and where the
+// e / Ke scratch lives.  Preference: 8 warps per block and two blocks per SM (16 resident warps).
+void banded_pick_config(int D, int K, int NT, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
     const int RED = 4 + K;
-    DW = D;
-    for (int g = 4; g >= 1; g >>= 1) {
-        if (g * DW > 16) continue;
-        size_t red = (size_t)g * 8 * D * RED * sizeof(double);
-        size_t scr = banded_scratch_doubles_per_cta(g, D, NT) * sizeof(double);
-        if (scr + red <= (size_t)smem_limit) { G = g; scratch_in_smem = 1; smem_bytes = scr + red; return; }
+    DW = D < 8 ? D : 8;
+    const int cand[6][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}, {4, 1}, {4, 2}};
+    int gmax = 4, hforce = 0;
+    if (const char* e = getenv("MAGI_FORCE_G")) gmax = atoi(e);
+    if (const char* e = getenv("MAGI_FORCE_H")) hforce = atoi(e);
+    const bool force_global = getenv("MAGI_FORCE_GLOBAL_SCRATCH") != nullptr;
+    for (int pass = 0; pass < 2 && !force_global; ++pass) {          // pass 0: two blocks per SM; pass 1: one block per SM
+        for (int i = 0; i < 4; ++i) {
+            int g = cand[i][0], hh = cand[i][1];
+            if (g > gmax || (hforce && hh != hforce)) continue;
+            if (hh > 1 && NT < 4 * hh) continue;
+            if (g * DW * hh > 8) continue;
+            size_t red = (size_t)g * 8 * D * hh * RED * sizeof(double);
+            size_t scr = banded_scratch_doubles_per_cta(g, D, NT) * sizeof(double);
+            size_t lim = pass == 0 ? (size_t)(smem_limit + 1024) / 2 - 1024 : (size_t)smem_limit;
+            if (scr + red <= lim) { G = g; H = hh; scratch_in_smem = 1; smem_bytes = scr + red; return; }
+        }
     }
-    G = 4;
-    while (G * DW > 16) G >>= 1;
-    if (G < 1) { G = 1; DW = 16; }
+    G = 2; H = (NT >= 8) ? 2 : 1;
+    while (G * DW * H > 8 && H > 1) H >>= 1;
+    while (G * DW * H > 8 && G > 1) G >>= 1;
     scratch_in_smem = 0;
-    smem_bytes = (size_t)G * 8 * D * RED * sizeof(double);
+    smem_bytes = (size_t)G * 8 * D * H * RED * sizeof(double);
 }
 
 template <int MODEL, int HB>
@@ -365,7 +453,7 @@ static cudaError_t launch_one(const BandedArgs& a, int DW, size_t smem_bytes, cu
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int threads = a.G * DW * 32;
+    const int threads = a.G * DW * a.H * 32;
     const int blocks = (a.n_chains + a.G * 8 - 1) / (a.G * 8);
     kern<<<blocks, threads, smem_bytes, st>>>(a);
     return cudaGetLastError();

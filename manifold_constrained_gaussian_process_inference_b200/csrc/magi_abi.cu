@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <new>
 #include "magi_common.cuh"
@@ -126,7 +127,7 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
     if (!h->dense_mode) {
         size_t fsz = (size_t)4 * h->D * h->geom.NT * h->geom.NCH * 32;
         if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
-        banded_pick_config(h->D, h->K, h->geom.NT, h->smem_limit, h->G, h->DW, h->scratch_in_smem, h->smem_bytes);
+        banded_pick_config(h->D, h->K, h->geom.NT, h->smem_limit, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
     }
     if (h->setup_mode != MAGI_SETUP_INJECT) {
         rc = run_device_setup(h);
@@ -183,14 +184,29 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     rc = ensure_scratch(h, n_chains);
     if (rc) return rc;
     BandedArgs a;
-    a.n = h->n; a.D = h->D; a.K = h->K; a.P = h->P; a.n_chains = n_chains; a.NT = h->geom.NT; a.G = h->G;
+    a.n = h->n; a.D = h->D; a.K = h->K; a.P = h->P; a.n_chains = n_chains; a.NT = h->geom.NT; a.G = h->G; a.H = h->H;
     a.sigma_is_fixed = h->sigma_is_fixed; a.sigma_invalid = h->sigma_invalid; a.scratch_in_smem = h->scratch_in_smem;
     a.pitch = pitch; a.params = params_dev; a.ll = ll_dev; a.grad = grad_dev;
     a.fragtab = h->d_fragtab; a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
     for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
     a.scratch = h->d_scratch;
+    a.dbg = nullptr;
+    static const bool dbg_clocks = getenv("MAGI_DBG_CLOCKS") != nullptr;
+    long long* d_dbg = nullptr;
+    const int nblk = (n_chains + h->G * 8 - 1) / (h->G * 8), nwarp = h->G * h->DW * h->H;
+    if (dbg_clocks) { cudaMalloc(&d_dbg, sizeof(long long) * 8 * nblk * nwarp); cudaMemset(d_dbg, 0, sizeof(long long) * 8 * nblk * nwarp); a.dbg = d_dbg; }
     CK(launch_banded_cfg(h->model, a, h->geom.HB, h->DW, h->smem_bytes, st), "banded_logpost_kernel launch");
     h->launches++;
+    if (dbg_clocks) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> v((size_t)8 * nblk * nwarp);
+        cudaMemcpy(v.data(), d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < nblk * nwarp; ++i) { for (int j = 0; j < 8; ++j) s[j] += (double)v[i * 8 + j]; }
+        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: P1=%.0f sync=%.0f P2=%.0f sync=%.0f P3=%.0f sync|fine_pre=%.0f fine_dmma=%.0f fine_point=%.0f\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
+                s[0] / (nblk * nwarp), s[1] / (nblk * nwarp), s[2] / (nblk * nwarp), s[3] / (nblk * nwarp), s[4] / (nblk * nwarp), s[5] / (nblk * nwarp), s[6] / (nblk * nwarp), s[7] / (nblk * nwarp));
+        cudaFree(d_dbg);
+    }
     return MAGI_OK;
 }
 

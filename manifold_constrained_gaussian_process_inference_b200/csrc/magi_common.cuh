@@ -37,7 +37,7 @@ inline BandGeom band_geom(int n, int b) {
 constexpr int kMaxHB = 8;   // band half-widths up to 32 run on the windowed DMMA kernel
 
 struct BandedArgs {
-    int n, D, K, P, n_chains, NT, G, sigma_is_fixed, sigma_invalid, scratch_in_smem;
+    int n, D, K, P, n_chains, NT, G, H, sigma_is_fixed, sigma_invalid, scratch_in_smem;
     long long pitch;
     const double* params;
     double* ll;
@@ -49,13 +49,14 @@ struct BandedArgs {
     double beta[3];
     double inv_beta[3];
     double* scratch;            // global Ke scratch when it does not fit shared memory
+    long long* dbg;             // optional per-warp phase clocks (MAGI_DBG_CLOCKS=1; null in production)
 };
 
 // launches (defined in the .cu files)
 cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
                                  int n, int b, int D, cudaStream_t st);
 size_t banded_scratch_doubles_per_cta(int G, int D, int NT);
-void banded_pick_config(int model_D, int model_K, int NT, int smem_limit, int& G, int& DW, int& scratch_in_smem, size_t& smem_bytes);
+void banded_pick_config(int model_D, int model_K, int NT, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes);
 bool model_dims(int model, int& D, int& K);
 
 }  // namespace magi

@@ -31,7 +31,7 @@ struct magi_handle {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int smem_limit = 0, sm_count = 148;
-    int G = 4, DW = 1, scratch_in_smem = 1;
+    int G = 2, H = 1, DW = 1, scratch_in_smem = 1;
     size_t smem_bytes = 0;
     std::vector<int> repaired_c, repaired_k;
     void* hmc = nullptr;     // on-device sampler state (hmc.cu)
