@@ -1,0 +1,288 @@
+// K2: dense-mode evaluation.  Used when the band does not fit the windowed DMMA kernel (half-width > 32, in particular
+// bandsize = n-1, which the reference treats as "dense": BandedMatrix == dense, test/test_gp.jl:551-585) and for models
+// with many components (Lorenz-96).  Same mathematics as K1 (src/likelihoods.jl:43-257, interface.jl:176-267); the four
+// products per dimension are (n x n) . (n x chains) GEMMs on DMMA tiles (gemm_f64.cu) that read the chain state through
+// a strided view of the chain-contiguous parameter buffer, with the ODE / gradient work in two pointwise kernels:
+//   MX = m~ X, CX = C~ X          (2 batched GEMMs over d)
+//   E  = f(X, theta) - MX          (pointwise)
+//   KE = K~ E                      (GEMM)
+//   MT = m~^T KE                   (GEMM)
+//   gradient, reductions, sigma transform and guards (one block per chain)
+#include <cmath>
+#include "magi_internal.cuh"
+#include "gemm_f64.cuh"
+#include "ode_models.cuh"
+
+namespace magi {
+
+#define DCK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_error(e__, what); } while (0)
+
+// band table (diagonal-major) -> dense n x n column-major with zeros outside the band (mat2band semantics)
+__global__ void band_to_dense_kernel(const double* __restrict__ band, double* __restrict__ dense, int n, int b) {
+    const int d = blockIdx.z;
+    const size_t nn = (size_t)n * n, tab = (size_t)(2 * b + 1) * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nn; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        const int off = j - i;
+        dense[d * nn + idx] = (off >= -b && off <= b) ? band[d * tab + (size_t)(b + off) * n + i] : 0.0;
+    }
+}
+
+// ---- model access through a loader (x(dd) = state component dd at this (time, chain)) so that Lorenz-96 with D = 64
+// never materialises a 64-entry register array ----
+template <int MODEL> struct DenseOde {
+    static constexpr int K = Ode<MODEL>::K;
+    template <class X> __device__ static double f(int d, X x, const double* th, int) {
+        double xa[Ode<MODEL>::D];
+#pragma unroll
+        for (int i = 0; i < Ode<MODEL>::D; ++i) xa[i] = x(i);
+        return Ode<MODEL>::f(d, xa, th);
+    }
+    template <class X, class W> __device__ static void jx_col_sub(int j, X x, W w, const double* th, int, double& g) {
+        double xa[Ode<MODEL>::D], wa[Ode<MODEL>::D];
+#pragma unroll
+        for (int i = 0; i < Ode<MODEL>::D; ++i) { xa[i] = x(i); wa[i] = w(i); }
+        Ode<MODEL>::jx_col_sub(j, xa, th, wa, g);
+    }
+    template <class X> __device__ static void jth_row_sub(int p, X x, const double* th, int, double w, double* acc) {
+        double xa[Ode<MODEL>::D];
+#pragma unroll
+        for (int i = 0; i < Ode<MODEL>::D; ++i) xa[i] = x(i);
+        Ode<MODEL>::jth_row_sub(p, xa, th, w, acc);
+    }
+};
+// Lorenz-96 (not in the reference; BASELINE config 4): x_i' = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F, cyclic.
+template <> struct DenseOde<MAGI_MODEL_L96> {
+    static constexpr int K = 1;
+    template <class X> __device__ static double f(int d, X x, const double* th, int D) {
+        const int p1 = (d + 1) % D, m1 = (d + D - 1) % D, m2 = (d + D - 2) % D;
+        return (x(p1) - x(m2)) * x(m1) - x(d) + th[0];
+    }
+    // column j of the Jacobian has four entries: rows j-1, j, j+1, j+2
+    template <class X, class W> __device__ static void jx_col_sub(int j, X x, W w, const double*, int D, double& g) {
+        const int jm2 = (j + D - 2) % D, jm1 = (j + D - 1) % D, jp1 = (j + 1) % D, jp2 = (j + 2) % D;
+        g -= x(jm2) * w(jm1);                  // d f_{j-1} / d x_j = x_{j-2}
+        g -= (-1.0) * w(j);                    // d f_j / d x_j = -1
+        g -= (x(jp2) - x(jm1)) * w(jp1);       // d f_{j+1} / d x_j = x_{j+2} - x_{j-1}
+        g -= (-x(jp1)) * w(jp2);               // d f_{j+2} / d x_j = -x_{j+1}
+    }
+    template <class X> __device__ static void jth_row_sub(int, X, const double*, int, double w, double* acc) { acc[0] -= w; }
+};
+
+template <int MODEL>
+__global__ void dense_e_kernel(const double* __restrict__ params, long long pitch, int n, int D, int n_chains,
+                               const double* MX, double* E) {   // E may alias MX (in place)
+    constexpr int K = DenseOde<MODEL>::K;
+    const int c = blockIdx.y;
+    const double* xp = params + (size_t)c * pitch;
+    double th[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    const size_t plane = (size_t)n * n_chains;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
+        for (int d = 0; d < D; ++d) {
+            const size_t o = (size_t)d * plane + (size_t)c * n + i;
+            E[o] = DenseOde<MODEL>::f(d, x, th, D) - MX[o];        // likelihoods.jl:130
+        }
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+    return r;
+}
+
+struct DenseGradArgs {
+    int n, D, K, P, n_chains, sigma_is_fixed, sigma_invalid;
+    long long pitch;
+    const double* params; double* ll; double* grad;
+    const double *E, *KE, *CX, *MT;
+    const double* yobs; const int* nobs; const double* sigma_init;
+    double beta[3], inv_beta[3];
+};
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) {
+    constexpr int K = DenseOde<MODEL>::K;
+    __shared__ double sh[8];
+    __shared__ int sbad;
+    const int c = blockIdx.x, n = a.n, D = a.D;
+    const double* xp = a.params + (size_t)c * a.pitch;
+    double* gp = a.grad ? a.grad + (size_t)c * a.pitch : nullptr;
+    const size_t plane = (size_t)n * a.n_chains, base = (size_t)c * n;
+    const int nxt = n * D + K, P = a.P;
+    if (a.sigma_invalid) {                                            // interface.jl:192-195
+        if (threadIdx.x == 0) a.ll[c] = -INFINITY;
+        if (gp) for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = NAN;
+        return;
+    }
+    double th[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    if (threadIdx.x == 0) sbad = 0;
+    const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
+    double gth[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) gth[i] = 0.0;
+    double ll = 0.0, prior = 0.0;
+    bool bad = false, bad2 = false;
+    for (int d = 0; d < D; ++d) {
+        double s;
+        if (a.sigma_is_fixed) s = a.sigma_init[d];
+        else {
+            const double raw = xp[nxt + d];
+            const double cl = fmin(fmax(raw, -15.0), 15.0);           // interface.jl:200
+            s = isnan(raw) ? raw : exp(cl);
+            prior += isnan(raw) ? raw : cl;
+        }
+        const double s2 = s * s, inv_sig2 = 1.0 / s2;
+        const double* Ed = a.E + (size_t)d * plane + base;
+        const double* KEd = a.KE + (size_t)d * plane + base;
+        const double* CXd = a.CX + (size_t)d * plane + base;
+        const double* MTd = a.MT + (size_t)d * plane + base;
+        const double* yd = a.yobs + (size_t)d * n;
+        double eke = 0.0, xcx = 0.0, sse = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
+            auto w = [&](int dd) { return a.KE[(size_t)dd * plane + base + i] * inv_b1; };   // likelihoods.jl:201
+            const double xdv = xp[(size_t)d * n + i], y = yd[i], cx = CXd[i], ke = KEd[i];
+            const bool fin = isfinite(y);
+            const double e0 = fin ? xdv - y : 0.0;
+            double gv = 0.0;
+            if (fin) gv -= (e0 * inv_sig2) * inv_b3;                   // likelihoods.jl:179
+            gv -= cx * inv_b2;                                         // :186
+            gv += MTd[i] * inv_b1;                                     // :194
+            DenseOde<MODEL>::jx_col_sub(d, x, w, th, D, gv);           // :214-216
+            DenseOde<MODEL>::jth_row_sub(d, x, th, D, ke * inv_b1, gth);   // :219-221
+            eke += Ed[i] * ke;
+            xcx += xdv * cx;
+            sse += e0 * e0;
+            bad |= !isfinite(gv);
+            if (gp) gp[(size_t)d * n + i] = gv;
+        }
+        eke = block_sum(eke, sh); xcx = block_sum(xcx, sh); sse = block_sum(sse, sh);
+        const int nobs = a.nobs[d];
+        double ll_obs = -0.5 * sse / s2;                               // likelihoods.jl:139
+        if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);    // :141
+        ll += ll_obs / a.beta[2];
+        ll += (-0.5 * eke) / a.beta[0];
+        ll += (-0.5 * xcx) / a.beta[1];
+        const double gsig = (s > 0 && nobs > 0) ? (sse / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
+        bad |= !isfinite(gsig);
+        if (!a.sigma_is_fixed) {
+            const double gls = gsig * s + 1.0;                         // interface.jl:249-253
+            bad2 |= !isfinite(gls);
+            if (gp && threadIdx.x == 0) gp[nxt + d] = gls;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) { gth[i] = block_sum(gth[i], sh); bad |= !isfinite(gth[i]); }
+    bad |= !isfinite(ll);
+    if (bad) atomicOr(&sbad, 1);
+    if (bad2) atomicOr(&sbad, 2);
+    __syncthreads();
+    const int fl = sbad;
+    if (fl & 1) {                                                      // interface.jl:222-226
+        if (threadIdx.x == 0) a.ll[c] = -INFINITY;
+        if (gp) for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = 0.0;
+        return;
+    }
+    if (threadIdx.x == 0) a.ll[c] = a.sigma_is_fixed ? ll : ll + prior;
+    if (gp) {
+        if (fl & 2) { for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = 0.0; }   // interface.jl:260-264
+        else if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) gp[n * D + i] = gth[i];
+        }
+    }
+}
+
+template <int MODEL>
+static int dense_pointwise(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad,
+                           const double* MX, double* E, const double* KE, const double* CX, const double* MT, int stage, cudaStream_t st) {
+    if (stage == 0) {
+        dim3 grid((h->n + 255) / 256, n_chains);
+        dense_e_kernel<MODEL><<<grid, 256, 0, st>>>(params, pitch, h->n, h->D, n_chains, MX, E);
+    } else {
+        DenseGradArgs a;
+        a.n = h->n; a.D = h->D; a.K = h->K; a.P = h->P; a.n_chains = n_chains; a.sigma_is_fixed = h->sigma_is_fixed; a.sigma_invalid = h->sigma_invalid;
+        a.pitch = pitch; a.params = params; a.ll = ll; a.grad = grad; a.E = E; a.KE = KE; a.CX = CX; a.MT = MT;
+        a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
+        for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
+        dense_grad_kernel<MODEL><<<n_chains, 256, 0, st>>>(a);
+    }
+    DCK(cudaGetLastError(), "dense pointwise kernel");
+    h->launches++;
+    return MAGI_OK;
+}
+
+static int dense_pointwise_dispatch(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad,
+                                    const double* MX, double* E, const double* KE, const double* CX, const double* MT, int stage, cudaStream_t st) {
+    switch (h->model) {
+#define MAGI_CASE(M) case M: return dense_pointwise<M>(h, n_chains, params, pitch, ll, grad, MX, E, KE, CX, MT, stage, st);
+    MAGI_CASE(MAGI_MODEL_FN) MAGI_CASE(MAGI_MODEL_HES1) MAGI_CASE(MAGI_MODEL_LV) MAGI_CASE(MAGI_MODEL_L96)
+    MAGI_CASE(MAGI_MODEL_HES1LOG) MAGI_CASE(MAGI_MODEL_HES1LOG_FIXG) MAGI_CASE(MAGI_MODEL_HES1LOG_FIXF) MAGI_CASE(MAGI_MODEL_HIV) MAGI_CASE(MAGI_MODEL_PTRANS)
+#undef MAGI_CASE
+    default: return set_error(MAGI_ERR_UNSUPPORTED, "dense mode: unknown model");
+    }
+}
+
+int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad, cudaStream_t st) {
+    const int n = h->n, D = h->D;
+    const size_t nn = (size_t)n * n, plane = (size_t)n * n_chains;
+    // dense (band-truncated) operators, rebuilt when the band tables change
+    if (!h->d_dense_ops) {
+        DCK(cudaMalloc(&h->d_dense_ops, sizeof(double) * 3 * nn * D), "cudaMalloc dense operators");
+        h->dense_band_dirty = true;
+    }
+    if (h->dense_band_dirty) {
+        size_t blocks = (nn + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+        for (int t = 0; t < 3; ++t) {
+            band_to_dense_kernel<<<dim3((unsigned)blocks, 1, D), 256, 0, st>>>(h->d_band[t], h->d_dense_ops + (size_t)t * nn * D, n, h->b);
+            h->launches++;
+        }
+        DCK(cudaGetLastError(), "band_to_dense_kernel");
+        h->dense_band_dirty = false;
+    }
+    const size_t need = 4 * plane * D;
+    if (need > h->dense_work_cap) {
+        if (h->d_dense_work) cudaFree(h->d_dense_work);
+        h->d_dense_work = nullptr; h->dense_work_cap = 0;
+        DCK(cudaMalloc(&h->d_dense_work, sizeof(double) * need), "cudaMalloc dense work space");
+        h->dense_work_cap = need;
+    }
+    double* MXE = h->d_dense_work;            // MX, then E in place
+    double* KE = MXE + plane * D;
+    double* CX = KE + plane * D;
+    double* MT = CX + plane * D;
+    const double* Cinv = h->d_dense_ops;                  // [D][n x n]
+    const double* Mphi = h->d_dense_ops + nn * D;
+    const double* Kinv = h->d_dense_ops + 2 * nn * D;
+    auto gemm = [&](const double* A, bool tA, const double* B, long long rsB, long long csB, long long bsB, double* C) {
+        GemmArgs g{};
+        g.A = A; g.rsA = tA ? n : 1; g.csA = tA ? 1 : n; g.bsA1 = (long long)nn; g.bsA2 = 0;
+        g.B = B; g.rsB = rsB; g.csB = csB; g.bsB1 = bsB; g.bsB2 = 0;
+        g.C = C; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = 0;
+        g.M = n; g.N = n_chains; g.K = n; g.nb1 = 1 << 30; g.alpha = 1.0; g.beta = 0.0;
+        cudaError_t e = launch_gemm(g, D, st);
+        h->launches++;
+        return e;
+    };
+    // X_d(i, c) = params[c * pitch + d * n + i]
+    DCK(gemm(Mphi, false, params, 1, pitch, n, MXE), "dense gemm m~ X");
+    DCK(gemm(Cinv, false, params, 1, pitch, n, CX), "dense gemm C~ X");
+    int rc = dense_pointwise_dispatch(h, n_chains, params, pitch, ll, grad, MXE, MXE, nullptr, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    DCK(gemm(Kinv, false, MXE, 1, n, (long long)plane, KE), "dense gemm K~ E");
+    DCK(gemm(Mphi, true, KE, 1, n, (long long)plane, MT), "dense gemm m~^T KE");
+    return dense_pointwise_dispatch(h, n_chains, params, pitch, ll, grad, nullptr, MXE, KE, CX, MT, 1, st);
+}
+
+}  // namespace magi

@@ -26,6 +26,7 @@ struct magi_handle {
     double* d_scratch = nullptr;
     size_t scratch_cap = 0;
     // dense-mode work space
+    double* d_dense_ops = nullptr;     // band-truncated dense Cinv~, mphi~, Kinv~ ([3][D][n x n]) for the dense path
     double* d_dense_work = nullptr;
     size_t dense_work_cap = 0;
     cudaStream_t stream = nullptr;

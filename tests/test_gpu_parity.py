@@ -72,6 +72,9 @@ def test_reference_hes1_case(pkg):
     ("fn", 64, 32, 16, {}),
     ("lv", 81, 20, 10, {"T": 4.0}),
     ("hes1", 33, 5, 13, {}),
+    ("fn", 120, 119, 7, {"T": 12.0}),                       # dense path: band = n-1 (GEMM formulation)
+    ("lv", 150, 40, 5, {"T": 6.0}),                         # dense path with a partial band (half-width > 32)
+    ("hes1", 70, 69, 4, {}),
 ])
 def test_batched_parity_random(pkg, model, n, b, nc, kw):
     prob = H.make_problem(model=model, n=n, b=b, n_chains=nc, seed=n + b, **kw)
@@ -131,3 +134,22 @@ def test_tempering_changes_result(pkg):
     l0, g0 = H.cuda_target(pkg, p0).logdensity_and_gradient_batched(p0["params"])
     l1, g1 = H.cuda_target(pkg, p1).logdensity_and_gradient_batched(p1["params"])
     assert np.all(l0 != l1) and not np.allclose(g0, g1, atol=1e-6, rtol=1e-6)
+
+
+def test_lorenz96_dense_path(pkg):
+    """Lorenz-96 (D = 16 here; BASELINE config 4 uses 64) is not in the reference: oracle = derivation, FD-checked in
+    tests/test_oracle_pins.py.  Runs on the GEMM path with band-truncated operators."""
+    rng = np.random.default_rng(9)
+    n, D, b, nc = 48, 16, 10, 6
+    t = np.linspace(0.0, 2.0, n)
+    covs = [mo.calculate_gp_covariances(mo.MATERN52, [10.0 + d, 0.3 + 0.01 * d], t, b, jitter=1e-6) for d in range(D)]
+    Y = np.full((n, D), np.nan)
+    Y[::4] = 8.0 + rng.normal(size=(len(t[::4]), D))
+    tgt = mo.make_target(Y, covs, mo.MODEL_L96, np.full(D, 0.5), (1.0, 1.0, 1.0), False)
+    P = mo.dimension(tgt)
+    params = np.concatenate([8.0 + rng.normal(size=(nc, n * D)), 8.0 + 0.1 * rng.normal(size=(nc, 1)), np.log(0.5) + 0.1 * rng.normal(size=(nc, D))], axis=1)
+    prob = dict(target=tgt, params=params, covs=covs)
+    tg = H.cuda_target(pkg, prob)
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    ll_ref, g_ref = H.oracle_batched(prob)
+    H.assert_parity(ll, g, ll_ref, g_ref, "lorenz96")
