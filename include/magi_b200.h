@@ -130,6 +130,23 @@ int magi_gp_covariances(int kernel_id, const double* phi, const double* tvec, in
                         double* Cdoubleprime, double* mphi, double* Kphi, double* Kinv, double* CinvBand,
                         double* mphiBand, double* KinvBand, int* repaired);
 
+/* ---- on-device batched HMC: the sampler loop of run_nuts_sampler (src/samplers.jl:114-194:
+ * diagonal Euclidean metric, leapfrog, Stan-style step-size and metric adaptation) with the chain state resident in HBM.
+ * Static trajectories of n_leapfrog steps; every leapfrog step is one evaluation of the hot path for every chain.
+ * Random numbers are Philox streams keyed by (seed, chain_id_offset + chain), so a run does not depend on how the
+ * chains are sharded over GPUs. */
+int magi_hmc_init(magi_handle* h, int n_chains, const double* params0 /* P x n_chains */, unsigned long long seed,
+                  double step_size0, long long chain_id_offset);
+int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream);
+int magi_hmc_reset_stats(magi_handle* h);
+int magi_hmc_get_state(magi_handle* h, double* params /* P x n_chains or NULL */, double* ll /* n_chains or NULL */);
+/* draws: [n_stored][n_chains][k + D + 1] = (theta, sigma, lp) like solve_magi's theta / sigma / lp (src/MagiJl.jl:633-771) */
+int magi_hmc_get_draws(magi_handle* h, double* out, long long max_iters, long long* n_stored);
+int magi_hmc_draws_dev(magi_handle* h, void** ptr_dev, long long* n_stored, int* n_chains, int* n_cols);
+int magi_hmc_get_stats(magi_handle* h, double* accept_rate, double* step_size, int* n_divergent, double* xmean /* nD x n_chains */,
+                       double* minv /* P */);
+long long magi_hmc_grad_evals(magi_handle* h);
+
 /* introspection used by bench.py / tests: number of kernel launches issued by this handle so far */
 long long magi_launch_count(const magi_handle* h);
 

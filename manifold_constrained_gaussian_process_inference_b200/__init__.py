@@ -7,10 +7,13 @@ from . import _lib
 from .kernels import Kernel, create_matern52_kernel, create_rbf_kernel
 from .ode_models import OdeSystem, get_ode_system, fn_system, hes1_system, lv_system, MODEL_IDS
 from .gaussian_process import GPCov, calculate_gp_covariances, mat2band
+from .samplers import run_hmc_sampler
+from .solver import solve_magi
+from . import diagnostics, distributed
 from .target import MagiTarget, dimension, capabilities, logdensity, logdensity_and_gradient, LogDensityOrder
 
 __all__ = [
     "Kernel", "create_matern52_kernel", "create_rbf_kernel", "OdeSystem", "get_ode_system", "fn_system", "hes1_system",
     "lv_system", "MODEL_IDS", "GPCov", "calculate_gp_covariances", "mat2band", "MagiTarget", "dimension", "capabilities",
-    "logdensity", "logdensity_and_gradient", "LogDensityOrder",
+    "logdensity", "logdensity_and_gradient", "LogDensityOrder", "run_hmc_sampler", "solve_magi", "diagnostics", "distributed",
 ]

@@ -41,7 +41,8 @@ EXPORTED = [
     "magi_last_error", "magi_version", "magi_create", "magi_destroy", "magi_dimension", "magi_capabilities_order",
     "magi_logdensity", "magi_logdensity_and_gradient", "magi_logdensity_and_gradient_batched",
     "magi_logdensity_and_gradient_batched_dev", "magi_get_matrix", "magi_set_band_tables", "magi_setup_status",
-    "magi_launch_count", "magi_gp_covariances",
+    "magi_launch_count", "magi_gp_covariances", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
+    "magi_hmc_get_state", "magi_hmc_get_draws", "magi_hmc_draws_dev", "magi_hmc_get_stats", "magi_hmc_grad_evals",
 ]
 
 
@@ -82,13 +83,16 @@ def _optional(L):
     if hasattr(L, "magi_gp_covariances"):
         L.magi_gp_covariances.argtypes = [ci, dp, dp, ci, ci, ctypes.c_double, ci, ci, ci, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, c_int_p]
     if hasattr(L, "magi_hmc_init"):
-        L.magi_hmc_init.argtypes = [vp, ci, dp, ctypes.c_ulonglong, ctypes.c_double, ci]
+        ll = ctypes.c_longlong
+        L.magi_hmc_init.argtypes = [vp, ci, dp, ctypes.c_ulonglong, ctypes.c_double, ll]
         L.magi_hmc_run.argtypes = [vp, ci, ci, ci, ctypes.c_double, ci, vp]
+        L.magi_hmc_reset_stats.argtypes = [vp]
         L.magi_hmc_get_state.argtypes = [vp, dp, dp]
-        L.magi_hmc_get_draws.argtypes = [vp, dp, ci]
-        L.magi_hmc_get_stats.argtypes = [vp, dp, dp, dp]
+        L.magi_hmc_get_draws.argtypes = [vp, dp, ll, ctypes.POINTER(ll)]
+        L.magi_hmc_draws_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ll), c_int_p, c_int_p]
+        L.magi_hmc_get_stats.argtypes = [vp, dp, dp, c_int_p, dp, dp]
         L.magi_hmc_grad_evals.argtypes = [vp]
-        L.magi_hmc_grad_evals.restype = ctypes.c_longlong
+        L.magi_hmc_grad_evals.restype = ll
 
 
 def check(rc):

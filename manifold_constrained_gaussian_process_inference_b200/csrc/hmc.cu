@@ -1,0 +1,406 @@
+// On-device batched HMC: the caller either side of the hot path.
+// The reference drives ONE chain with AdvancedHMC NUTS from the host (run_nuts_sampler, src/samplers.jl:114-194:
+// DiagEuclideanMetric, Leapfrog, StanHMCAdaptor(MassMatrixAdaptor, StepSizeAdaptor(delta))), calling
+// logdensity_and_gradient once per leapfrog step.  Doing that for thousands of chains through PCIe costs ~0.5 ms per step
+// against tens of microseconds of kernel, so the state stays resident in HBM and a transition is a short sequence of
+// launches on one stream:
+//   momentum refresh (Philox, keyed by global chain id => results do not depend on how chains are sharded over GPUs)
+//   L x [ p += eps/2 g ; q += eps Minv p ; gradient (K1/K2) ; p += eps/2 g ]   (the two half kicks are fused)
+//   Metropolis accept/reject per chain, Nesterov dual averaging of eps per chain (Stan / AdvancedHMC defaults:
+//   gamma 0.05, t0 10, kappa 0.75, mu = log(10 eps0)), pooled diagonal metric from cross-chain variances in Stan-style
+//   doubling windows.  Static trajectory length (batched NUTS would diverge per chain; a later row).
+#include <cmath>
+#include <cstdio>
+#include "magi_internal.cuh"
+
+namespace magi {
+
+#define HCK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_error(e__, what); } while (0)
+
+struct HmcState {
+    int n_chains = 0, P = 0, n_draw_cols = 0;
+    long long chain_offset = 0;
+    unsigned long long seed = 0;
+    long long iter = 0;               // transitions done so far (RNG counter)
+    long long grad_evals = 0;
+    double *q = nullptr, *p = nullptr, *g = nullptr, *ll = nullptr;        // current position / momentum / gradient / log density
+    double *q0 = nullptr, *g0 = nullptr, *ll0 = nullptr, *h0 = nullptr;    // start of the trajectory
+    double *minv = nullptr;                                              // diagonal inverse metric (shared by all chains)
+    double *eps = nullptr, *da = nullptr;                                // per-chain step size and dual-averaging state [5]
+    double *acc_sum = nullptr;                                           // per-chain sum of acceptance probabilities
+    int *n_div = nullptr;
+    double *wsum = nullptr, *wsq = nullptr;                              // pooled window accumulators [P]
+    long long wcount = 0;
+    double *draws = nullptr; long long draws_cap = 0, n_draws = 0;       // [n_draws][n_chains][k + D + 1]
+    double *xsum = nullptr; long long xsum_count = 0;                    // per-chain running sum of vec(X) over kept draws
+    long long acc_count = 0;
+};
+
+// ---- Philox4x32-10 counter RNG ----
+__device__ __forceinline__ void philox4x32(unsigned int c[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned int n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double u01(unsigned int a, unsigned int b) {   // (0, 1)
+    const unsigned long long v = ((unsigned long long)a << 21) ^ (unsigned long long)b;   // 53 bits
+    return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+// two standard normals for (chain, iteration, pair index)
+__device__ __forceinline__ void normal_pair(unsigned long long seed, long long chain, long long iter, unsigned int pair, unsigned int stream,
+                                            double& z0, double& z1) {
+    unsigned int c[4] = {pair, stream, (unsigned int)iter, (unsigned int)(iter >> 32)};
+    philox4x32(c, (unsigned int)(seed ^ (unsigned long long)chain), (unsigned int)((seed >> 32) ^ ((unsigned long long)chain >> 32) ^ 0x5851F42Du));
+    const double u1 = u01(c[0], c[1]), u2 = u01(c[2], c[3]);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, co;
+    sincospi(2.0 * u2, &s, &co);
+    z0 = r * co; z1 = r * s;
+}
+
+// momentum refresh + snapshot of the trajectory start + first half kick + drift
+__global__ void hmc_begin_kernel(HmcState s, int P) {
+    const long long c = blockIdx.x;
+    const double eps = s.eps[c];
+    double kin = 0.0;
+    const size_t base = (size_t)c * P;
+    for (int i2 = blockIdx.y * blockDim.x + threadIdx.x; 2 * i2 < P; i2 += gridDim.y * blockDim.x) {
+        double z[2];
+        normal_pair(s.seed, c + s.chain_offset, s.iter, (unsigned int)i2, 0u, z[0], z[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = 2 * i2 + u;
+            if (i < P) {
+                const double mi = s.minv[i];
+                double p = z[u] * rsqrt(mi);                 // p ~ N(0, M), M = 1 / Minv
+                kin += 0.5 * p * p * mi;
+                const double q = s.q[base + i], g = s.g[base + i];
+                s.q0[base + i] = q; s.g0[base + i] = g;
+                p += 0.5 * eps * g;
+                s.p[base + i] = p;
+                s.q[base + i] = q + eps * mi * p;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s.h0[c], kin);
+}
+
+// h0[c] = -ll[c] (before the kinetic energy is accumulated); ll0 snapshot
+__global__ void hmc_prep_kernel(HmcState s) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < s.n_chains) { s.ll0[c] = s.ll[c]; s.h0[c] = -s.ll[c]; }
+}
+
+// between two gradient evaluations: p += eps g (two fused half kicks); q += eps Minv p
+__global__ void hmc_kick_drift_kernel(HmcState s, int P) {
+    const long long c = blockIdx.x;
+    const double eps = s.eps[c];
+    const size_t base = (size_t)c * P;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
+        const double p = s.p[base + i] + eps * s.g[base + i];
+        s.p[base + i] = p;
+        s.q[base + i] += eps * s.minv[i] * p;
+    }
+}
+
+struct HmcFinish {
+    int adapt, store, n_draw_cols, nD, K, D, sigma_is_fixed;
+    double delta, mu_scale;
+    int accumulate_window, accumulate_x;
+};
+
+// last half kick, Hamiltonian, accept/reject, dual averaging, draw storage (one block per chain)
+__global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcFinish f) {
+    __shared__ double sh[8];
+    __shared__ int s_accept;
+    const long long c = blockIdx.x;
+    const size_t base = (size_t)c * P;
+    const double eps = s.eps[c];
+    double kin = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double p = s.p[base + i] + 0.5 * eps * s.g[base + i];
+        kin += 0.5 * p * p * s.minv[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = kin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double k1 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) k1 += sh[i];
+        const double h1 = -s.ll[c] + k1;
+        double a = exp(s.h0[c] - h1);
+        const bool divergent = !isfinite(h1) || !isfinite(a) && !(s.h0[c] - h1 > 0);
+        if (!isfinite(h1)) a = 0.0;
+        if (a > 1.0 || (isinf(a) && s.h0[c] - h1 > 0)) a = 1.0;
+        if (isnan(a)) a = 0.0;
+        double z0, z1;
+        normal_pair(s.seed, c + s.chain_offset, s.iter, 0u, 1u, z0, z1);
+        unsigned int cc[4] = {1u, 2u, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};
+        philox4x32(cc, (unsigned int)(s.seed ^ (unsigned long long)(c + s.chain_offset)), (unsigned int)(s.seed >> 32) ^ 0x2545F491u);
+        const double u = u01(cc[0], cc[1]);
+        s_accept = (u < a) ? 1 : 0;
+        s.acc_sum[c] += a;
+        if (divergent || (s.h0[c] - h1) < -1000.0) s.n_div[c] += 1;
+        if (f.adapt) {
+            // Nesterov dual averaging (Hoffman & Gelman 2014; AdvancedHMC/Stan defaults)
+            double* da = s.da + (size_t)c * 5;     // m, Hbar, log_eps_bar, mu, (unused)
+            const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
+            const double m = da[0] + 1.0;
+            const double eta = 1.0 / (m + t0);
+            const double hbar = (1.0 - eta) * da[1] + eta * (f.delta - a);
+            const double log_eps = da[3] - sqrt(m) / gamma * hbar;
+            const double w = pow(m, -kappa);
+            const double log_eps_bar = w * log_eps + (1.0 - w) * da[2];
+            da[0] = m; da[1] = hbar; da[2] = log_eps_bar;
+            s.eps[c] = exp(log_eps);
+        }
+    }
+    __syncthreads();
+    const bool acc = s_accept != 0;
+    if (!acc) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { s.q[base + i] = s.q0[base + i]; s.g[base + i] = s.g0[base + i]; }
+        if (threadIdx.x == 0) s.ll[c] = s.ll0[c];
+    }
+    __syncthreads();
+    if (f.accumulate_window) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const double q = s.q[base + i];
+            atomicAdd(&s.wsum[i], q);
+            atomicAdd(&s.wsq[i], q * q);
+        }
+    }
+    if (f.accumulate_x) for (int i = threadIdx.x; i < f.nD; i += blockDim.x) s.xsum[(size_t)c * f.nD + i] += s.q[base + i];
+    if (f.store && threadIdx.x < f.n_draw_cols) {
+        double* out = s.draws + ((size_t)s.n_draws * s.n_chains + c) * f.n_draw_cols;
+        const int j = threadIdx.x;
+        double v;
+        if (j < f.K) v = s.q[base + f.nD + j];                                        // theta
+        else if (j < f.K + f.D) {                                                     // sigma = exp(clamped log sigma) (MagiJl.jl:696)
+            if (f.sigma_is_fixed) v = nan("");
+            else v = exp(fmin(fmax(s.q[base + f.nD + j], -15.0), 15.0));
+        } else v = s.ll[c];                                                           // lp
+        out[j] = v;
+    }
+}
+
+__global__ void hmc_window_finish_kernel(HmcState s, int P, double count, int reset_only) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) {
+        if (!reset_only && count > 1.0) {
+            const double mean = s.wsum[i] / count;
+            double var = (s.wsq[i] - count * mean * mean) / (count - 1.0);
+            if (!(var > 0.0) || !isfinite(var)) var = 1.0;
+            // Stan's shrinkage towards unit metric; count here is chains x iterations, so it is a light touch
+            const double nn = count;
+            s.minv[i] = (nn / (nn + 5.0)) * var + 1e-3 * (5.0 / (nn + 5.0));
+        }
+        s.wsum[i] = 0.0; s.wsq[i] = 0.0;
+    }
+}
+
+__global__ void hmc_restart_da_kernel(HmcState s, int finalize) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < s.n_chains) {
+        double* da = s.da + (size_t)c * 5;
+        if (finalize) { if (da[0] > 0) s.eps[c] = exp(da[2]); }       // use the averaged step size after warm-up
+        else { da[0] = 0.0; da[1] = 0.0; da[2] = 0.0; da[3] = log(10.0 * s.eps[c]); }
+    }
+}
+
+__global__ void fill_double_kernel(double* p, size_t nel, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nel; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void hmc_free(magi_handle* h) {
+    HmcState* s = (HmcState*)h->hmc;
+    if (!s) return;
+    double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->draws, s->xsum};
+    for (double* p : ptrs) if (p) cudaFree(p);
+    if (s->n_div) cudaFree(s->n_div);
+    delete s;
+    h->hmc = nullptr;
+}
+
+}  // namespace magi
+
+using namespace magi;
+
+extern "C" int magi_hmc_init(magi_handle* h, int n_chains, const double* params0, unsigned long long seed, double step_size0,
+                             long long chain_id_offset) {
+    if (!h || !params0 || n_chains <= 0 || !(step_size0 > 0)) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_init: bad argument");
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    hmc_free(h);
+    HmcState* s = new HmcState();
+    h->hmc = s;
+    const int P = h->P;
+    s->n_chains = n_chains; s->P = P; s->seed = seed; s->chain_offset = chain_id_offset;
+    s->n_draw_cols = h->K + h->D + 1;
+    const size_t NP = (size_t)n_chains * P;
+    double** big[] = {&s->q, &s->p, &s->g, &s->q0, &s->g0};
+    for (double** b : big) HCK(cudaMalloc(b, sizeof(double) * NP), "cudaMalloc hmc state");
+    double** small[] = {&s->ll, &s->ll0, &s->h0, &s->eps, &s->acc_sum};
+    for (double** b : small) HCK(cudaMalloc(b, sizeof(double) * n_chains), "cudaMalloc hmc per-chain");
+    HCK(cudaMalloc(&s->da, sizeof(double) * 5 * n_chains), "cudaMalloc da");
+    HCK(cudaMalloc(&s->n_div, sizeof(int) * n_chains), "cudaMalloc n_div");
+    HCK(cudaMalloc(&s->minv, sizeof(double) * P), "cudaMalloc minv");
+    HCK(cudaMalloc(&s->wsum, sizeof(double) * P), "cudaMalloc wsum");
+    HCK(cudaMalloc(&s->wsq, sizeof(double) * P), "cudaMalloc wsq");
+    HCK(cudaMalloc(&s->xsum, sizeof(double) * (size_t)n_chains * h->n * h->D), "cudaMalloc xsum");
+    cudaStream_t st = h->stream;
+    HCK(cudaMemcpyAsync(s->q, params0, sizeof(double) * NP, cudaMemcpyHostToDevice, st), "H2D initial state");
+    fill_double_kernel<<<64, 256, 0, st>>>(s->minv, P, 1.0);
+    fill_double_kernel<<<64, 256, 0, st>>>(s->eps, n_chains, step_size0);
+    HCK(cudaMemsetAsync(s->acc_sum, 0, sizeof(double) * n_chains, st), "memset");
+    HCK(cudaMemsetAsync(s->n_div, 0, sizeof(int) * n_chains, st), "memset");
+    HCK(cudaMemsetAsync(s->wsum, 0, sizeof(double) * P, st), "memset");
+    HCK(cudaMemsetAsync(s->wsq, 0, sizeof(double) * P, st), "memset");
+    HCK(cudaMemsetAsync(s->xsum, 0, sizeof(double) * (size_t)n_chains * h->n * h->D, st), "memset");
+    hmc_restart_da_kernel<<<(n_chains + 255) / 256, 256, 0, st>>>(*s, 0);
+    h->launches += 3;
+    int rc = eval_dev(h, n_chains, s->q, P, s->ll, s->g, st);
+    if (rc) return rc;
+    s->grad_evals += n_chains;
+    HCK(cudaStreamSynchronize(st), "hmc init sync");
+    return MAGI_OK;
+}
+
+// Runs n_iter transitions of n_leapfrog steps.  adapt != 0: warm-up (dual averaging towards target_accept and windowed
+// metric adaptation over these n_iter iterations).  store_draws != 0: appends (theta, sigma, lp) of every chain per iteration.
+extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream_) {
+    if (!h || !h->hmc || n_iter < 0 || n_leapfrog < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_run: bad argument (call magi_hmc_init first)");
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    HmcState* s = (HmcState*)h->hmc;
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;
+    const int P = s->P, nc = s->n_chains;
+    if (store_draws) {
+        const long long need = s->n_draws + n_iter;
+        if (need > s->draws_cap) {
+            double* nd = nullptr;
+            HCK(cudaMalloc(&nd, sizeof(double) * (size_t)need * nc * s->n_draw_cols), "cudaMalloc draws");
+            if (s->draws) { HCK(cudaMemcpyAsync(nd, s->draws, sizeof(double) * (size_t)s->n_draws * nc * s->n_draw_cols, cudaMemcpyDeviceToDevice, st), "copy draws"); HCK(cudaStreamSynchronize(st), "sync"); cudaFree(s->draws); }
+            s->draws = nd; s->draws_cap = need;
+        }
+    }
+    // Stan-style windows over the warm-up: initial fast buffer, doubling slow windows, terminal fast buffer
+    int init_buf = 75, term_buf = 50, base_win = 25;
+    if (adapt && n_iter < 150) { init_buf = (int)(0.15 * n_iter); term_buf = (int)(0.10 * n_iter); base_win = n_iter - init_buf - term_buf; }
+    int win_end = init_buf + base_win, win_size = base_win;
+    if (adapt) { int rem = n_iter - term_buf - win_end; if (rem < 2 * win_size) win_end = n_iter - term_buf; }
+    const dim3 egrid(nc, (P + 255) / 256 > 8 ? 8 : (P + 255) / 256);
+    HmcFinish f;
+    f.adapt = adapt; f.n_draw_cols = s->n_draw_cols; f.nD = h->n * h->D; f.K = h->K; f.D = h->D; f.sigma_is_fixed = h->sigma_is_fixed;
+    f.delta = target_accept; f.mu_scale = 10.0;
+    for (int it = 0; it < n_iter; ++it) {
+        hmc_prep_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s);
+        hmc_begin_kernel<<<egrid, 128, 0, st>>>(*s, P);
+        h->launches += 2;
+        for (int l = 0; l < n_leapfrog; ++l) {
+            int rc = eval_dev(h, nc, s->q, P, s->ll, s->g, st);
+            if (rc) return rc;
+            s->grad_evals += nc;
+            if (l + 1 < n_leapfrog) { hmc_kick_drift_kernel<<<egrid, 256, 0, st>>>(*s, P); h->launches++; }
+        }
+        const bool in_slow = adapt && it >= init_buf && it < n_iter - term_buf;
+        f.store = store_draws; f.accumulate_window = in_slow ? 1 : 0; f.accumulate_x = store_draws ? 1 : 0;
+        hmc_finish_kernel<<<nc, 256, 0, st>>>(*s, P, f);
+        h->launches++;
+        s->iter++;
+        if (store_draws) { s->n_draws++; s->xsum_count++; }
+        s->acc_count++;
+        if (in_slow) {
+            s->wcount += nc;
+            if (it + 1 == win_end) {
+                hmc_window_finish_kernel<<<(P + 255) / 256, 256, 0, st>>>(*s, P, (double)s->wcount, 0);
+                hmc_restart_da_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s, 0);
+                h->launches += 2;
+                s->wcount = 0;
+                win_size *= 2;
+                int next_end = win_end + win_size;
+                if (n_iter - term_buf - next_end < 2 * win_size) next_end = n_iter - term_buf;
+                win_end = next_end;
+            }
+        }
+    }
+    if (adapt && n_iter > 0) { hmc_restart_da_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s, 1); h->launches++; }
+    HCK(cudaGetLastError(), "hmc kernels");
+    HCK(cudaStreamSynchronize(st), "hmc sync");
+    return MAGI_OK;
+}
+
+extern "C" int magi_hmc_get_state(magi_handle* h, double* params, double* ll) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_get_state: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    if (params) HCK(cudaMemcpy(params, s->q, sizeof(double) * (size_t)s->n_chains * s->P, cudaMemcpyDeviceToHost), "D2H state");
+    if (ll) HCK(cudaMemcpy(ll, s->ll, sizeof(double) * s->n_chains, cudaMemcpyDeviceToHost), "D2H ll");
+    return MAGI_OK;
+}
+
+// draws: [n_stored][n_chains][k + D + 1] = (theta, sigma, lp); returns the number of stored iterations through *n_stored
+extern "C" int magi_hmc_get_draws(magi_handle* h, double* out, long long max_iters, long long* n_stored) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_get_draws: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    if (n_stored) *n_stored = s->n_draws;
+    if (out && s->n_draws > 0) {
+        const long long n = s->n_draws < max_iters ? s->n_draws : max_iters;
+        HCK(cudaMemcpy(out, s->draws, sizeof(double) * (size_t)n * s->n_chains * s->n_draw_cols, cudaMemcpyDeviceToHost), "D2H draws");
+    }
+    return MAGI_OK;
+}
+
+// device pointer to the draw store (for an NCCL all-gather without a host round trip) and its geometry
+extern "C" int magi_hmc_draws_dev(magi_handle* h, void** ptr, long long* n_stored, int* n_chains, int* n_cols) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_draws_dev: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    if (ptr) *ptr = s->draws;
+    if (n_stored) *n_stored = s->n_draws;
+    if (n_chains) *n_chains = s->n_chains;
+    if (n_cols) *n_cols = s->n_draw_cols;
+    return MAGI_OK;
+}
+
+// per-chain statistics: mean acceptance probability, current step size, divergences; xmean = posterior mean of vec(X) per chain
+extern "C" int magi_hmc_get_stats(magi_handle* h, double* accept_rate, double* step_size, int* n_divergent, double* xmean, double* minv) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_get_stats: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    const int nc = s->n_chains;
+    if (accept_rate) {
+        HCK(cudaMemcpy(accept_rate, s->acc_sum, sizeof(double) * nc, cudaMemcpyDeviceToHost), "D2H accept");
+        for (int i = 0; i < nc; ++i) accept_rate[i] /= (double)(s->acc_count > 0 ? s->acc_count : 1);
+    }
+    if (step_size) HCK(cudaMemcpy(step_size, s->eps, sizeof(double) * nc, cudaMemcpyDeviceToHost), "D2H eps");
+    if (n_divergent) HCK(cudaMemcpy(n_divergent, s->n_div, sizeof(int) * nc, cudaMemcpyDeviceToHost), "D2H ndiv");
+    if (xmean) {
+        const size_t nx = (size_t)nc * h->n * h->D;
+        HCK(cudaMemcpy(xmean, s->xsum, sizeof(double) * nx, cudaMemcpyDeviceToHost), "D2H xsum");
+        const double inv = 1.0 / (double)(s->xsum_count > 0 ? s->xsum_count : 1);
+        for (size_t i = 0; i < nx; ++i) xmean[i] *= inv;
+    }
+    if (minv) HCK(cudaMemcpy(minv, s->minv, sizeof(double) * s->P, cudaMemcpyDeviceToHost), "D2H minv");
+    return MAGI_OK;
+}
+
+extern "C" long long magi_hmc_grad_evals(magi_handle* h) {
+    if (!h || !h->hmc) return -1;
+    return ((HmcState*)h->hmc)->grad_evals;
+}
+
+// resets acceptance statistics and draw store (called between warm-up and sampling)
+extern "C" int magi_hmc_reset_stats(magi_handle* h) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_reset_stats: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    HCK(cudaMemset(s->acc_sum, 0, sizeof(double) * s->n_chains), "memset");
+    HCK(cudaMemset(s->n_div, 0, sizeof(int) * s->n_chains), "memset");
+    HCK(cudaMemset(s->xsum, 0, sizeof(double) * (size_t)s->n_chains * h->n * h->D), "memset");
+    s->acc_count = 0; s->n_draws = 0; s->xsum_count = 0;
+    return MAGI_OK;
+}

@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: chains shard across ranks with NO collective on the hot path (every rank rebuilds the identical
+GP tables locally); one all-gather of the retained scalar draws (θ, σ, lp) at the end of a run feeds R-hat / ESS
+(SURVEY.md section 8(e)).  torch.distributed is the transport: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_chains(n_chains_total: int, rank: int, world: int):
+    """Contiguous block partition: returns (first_chain, n_local).  The first chain id doubles as the RNG stream offset,
+    so the union of all ranks' chains is independent of the world size."""
+    base, rem = divmod(n_chains_total, world)
+    n_local = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n_local
+
+
+def allgather_draws(local_draws, group=None):
+    """local_draws: torch tensor (n_iter, n_local_chains, n_cols) on this rank's device (CUDA for NCCL, CPU for gloo).
+    Returns (n_iter, n_chains_total, n_cols) with chains in global order (ranks may hold different chain counts)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_draws
+    world = dist.get_world_size(group)
+    n_iter, n_local, n_cols = local_draws.shape
+    counts = [torch.zeros(1, dtype=torch.int64, device=local_draws.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=local_draws.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts)
+    pad = local_draws
+    if n_local < nmax:
+        pad = torch.cat([local_draws, local_draws.new_zeros((n_iter, nmax - n_local, n_cols))], dim=1)
+    pad = pad.contiguous()
+    out = local_draws.new_empty((world, n_iter, nmax, n_cols))
+    dist.all_gather_into_tensor(out, pad, group=group) if local_draws.is_cuda else dist.all_gather(list(out.unbind(0)), pad, group=group)
+    return torch.cat([out[r, :, :counts[r], :] for r in range(world)], dim=1)
+
+
+def device_draws_as_tensor(target):
+    """Zero-copy torch view of the on-device draw store of ``target`` (n_stored, n_chains, n_cols)."""
+    import torch
+    from .samplers import hmc_draws_device_view
+    ptr, ns, nc, ncol = hmc_draws_device_view(target)
+    if ns == 0:
+        return torch.empty((0, nc, ncol), dtype=torch.float64, device="cuda:%d" % target.device)
+
+    class _Holder:
+        pass
+    holder = _Holder()
+    holder.__cuda_array_interface__ = {"shape": (ns, nc, ncol), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device="cuda:%d" % target.device)
