@@ -1,0 +1,88 @@
+# MagiB200.jl -- the reference-side binding of libmagi_b200.so (see INTEGRATION.md).
+# NOT executed in this repository's CI: Julia is not available in the build image.  The same C ABI is exercised through
+# Python ctypes (tests/), entry point for entry point.
+#
+# Drop-in for the reference's MagiTarget (src/logdensityproblems_interface.jl:33-45): implements the four
+# LogDensityProblems methods the NUTS loop of src/samplers.jl:137-138 calls, by `ccall` into the shared library.
+module MagiB200
+
+using LogDensityProblems
+
+const LIB = get(ENV, "MAGI_B200_LIB", "libmagi_b200.so")
+
+struct MagiConfig                      # mirrors magi_config in include/magi_b200.h (field order matters)
+    n_times::Cint; n_dims::Cint; n_params_ode::Cint; kernel_id::Cint
+    bandsize::Cint; ode_model_id::Cint; sigma_is_fixed::Cint; setup_mode::Cint
+    max_chains::Cint; device::Cint
+    jitter::Cdouble
+    tvec::Ptr{Cdouble}; phi::Ptr{Cdouble}; yobs::Ptr{Cdouble}; sigma_init::Ptr{Cdouble}; prior_temperature::Ptr{Cdouble}
+end
+
+mutable struct MagiTargetGPU
+    h::Ptr{Cvoid}
+    P::Int
+    function MagiTargetGPU(h::Ptr{Cvoid})
+        t = new(h, Int(ccall((:magi_dimension, LIB), Cint, (Ptr{Cvoid},), h)))
+        finalizer(x -> ccall((:magi_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), t)
+        return t
+    end
+end
+
+last_error() = unsafe_string(ccall((:magi_last_error, LIB), Cstring, ()))
+
+const MODEL_IDS = Dict(:fn => 0, :hes1 => 1, :hes1log => 2, :hes1log_fixg => 3, :hes1log_fixf => 4, :hiv => 5, :ptrans => 6, :lv => 7, :lorenz96 => 8)
+
+"""
+    MagiTargetGPU(y_obs, t_obs, phi, model; sigma_init, prior_temperature, sigma_is_fixed, kernel, bandsize, jitter, ...)
+
+Replaces steps 4-5 of `solve_magi` (src/MagiJl.jl:456-520): the per-dimension `calculate_gp_covariances!` calls and the
+`MagiTarget(...)` construction.  `phi` is the 2 x D matrix of (variance; lengthscale) (src/MagiJl.jl:466-467).
+"""
+function MagiTargetGPU(y_obs::Matrix{Float64}, t_obs::Vector{Float64}, phi::Matrix{Float64}, model::Symbol;
+                       sigma_init::Vector{Float64}, prior_temperature::Vector{Float64} = [1.0, 1.0, 1.0],
+                       sigma_is_fixed::Bool = false, kernel::String = "matern52", bandsize::Int = 20, jitter::Float64 = 1e-6,
+                       n_params_ode::Int, setup_mode::Int = 0, max_chains::Int = 1, device::Int = 0)
+    n, D = size(y_obs)
+    cfg = Ref(MagiConfig(n, D, n_params_ode, kernel == "rbf" ? 1 : 0, bandsize, MODEL_IDS[model], sigma_is_fixed ? 1 : 0,
+                         setup_mode, max_chains, device, jitter, pointer(t_obs), pointer(phi), pointer(y_obs),
+                         pointer(sigma_init), pointer(prior_temperature)))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = GC.@preserve y_obs t_obs phi sigma_init prior_temperature ccall((:magi_create, LIB), Cint, (Ref{MagiConfig}, Ref{Ptr{Cvoid}}), cfg, out)
+    rc == 0 || error("magi_create failed: " * last_error())
+    return MagiTargetGPU(out[])
+end
+
+LogDensityProblems.dimension(t::MagiTargetGPU) = t.P
+LogDensityProblems.capabilities(::Type{MagiTargetGPU}) = LogDensityProblems.LogDensityOrder{1}()
+
+function LogDensityProblems.logdensity(t::MagiTargetGPU, params::AbstractVector{Float64})
+    ll = Ref{Cdouble}(0.0)
+    p = params isa Vector{Float64} ? params : collect(params)
+    rc = ccall((:magi_logdensity, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ref{Cdouble}), t.h, p, length(p), ll)
+    rc == 0 || error("magi_logdensity failed: " * last_error())
+    return ll[]
+end
+
+function LogDensityProblems.logdensity_and_gradient(t::MagiTargetGPU, params::AbstractVector{Float64})
+    ll = Ref{Cdouble}(0.0)
+    grad = Vector{Float64}(undef, t.P)
+    p = params isa Vector{Float64} ? params : collect(params)
+    rc = ccall((:magi_logdensity_and_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ref{Cdouble}, Ptr{Cdouble}), t.h, p, length(p), ll, grad)
+    rc == 0 || error("magi_logdensity_and_gradient failed: " * last_error())
+    return ll[], grad
+end
+
+"""
+Batched evaluation: `params` is a P x n_chains Matrix (one chain per column, the vectorised-HMC shape of AdvancedHMC).
+Returns (ll::Vector, grad::Matrix).
+"""
+function logdensity_and_gradient_batched(t::MagiTargetGPU, params::Matrix{Float64})
+    @assert size(params, 1) == t.P
+    nc = size(params, 2)
+    ll = Vector{Float64}(undef, nc); grad = similar(params)
+    rc = ccall((:magi_logdensity_and_gradient_batched, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), t.h, nc, params, ll, grad)
+    rc == 0 || error("batched evaluation failed: " * last_error())
+    return ll, grad
+end
+
+end # module
