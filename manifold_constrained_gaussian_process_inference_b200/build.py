@@ -46,6 +46,8 @@ def build(force: bool = False, fast: bool = False, verbose: bool = False) -> str
     os.makedirs(OBJDIR, exist_ok=True)
     extra = {"force": force, "defs": (["-DMAGI_FAST_BUILD"] if fast else []) + os.environ.get("MAGI_EXTRA_DEFS", "").split()}
     srcs = sources()
+    if fast:   # development builds: only the FN / Hes1 / LV kernels (the full build adds the other models)
+        srcs = [s_ for s_ in srcs if not (s_.startswith("banded_inst_") and s_ not in ("banded_inst_0.cu", "banded_inst_1.cu", "banded_inst_7.cu"))]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, extra), srcs))
     objs = [o for o, _ in res]

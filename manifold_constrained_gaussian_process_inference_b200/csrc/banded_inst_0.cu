@@ -1,0 +1,5 @@
+// K1 instantiations for ode_model_id 0 (all band half-widths); see banded_kernel.cuh
+#include "banded_kernel.cuh"
+namespace magi {
+cudaError_t launch_banded_model_0(const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st) { return launch_model<0>(a, HB, DW, smem_bytes, st); }
+}

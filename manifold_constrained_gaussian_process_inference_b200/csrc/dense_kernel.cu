@@ -31,7 +31,8 @@ __global__ void band_to_dense_kernel(const double* __restrict__ band, double* __
 // ---- model access through a loader (x(dd) = state component dd at this (time, chain)) so that Lorenz-96 with D = 64
 // never materialises a 64-entry register array ----
 template <int MODEL> struct DenseOde {
-    static constexpr int K = Ode<MODEL>::K;
+    static constexpr int K = Ode<MODEL>::K, KX = Ode<MODEL>::KX;
+    __device__ static void prepare(double* th) { Ode<MODEL>::prepare(th); }
     template <class X> __device__ static double f(int d, X x, const double* th, int) {
         double xa[Ode<MODEL>::D];
 #pragma unroll
@@ -53,7 +54,8 @@ template <int MODEL> struct DenseOde {
 };
 // Lorenz-96 (not in the reference; BASELINE config 4): x_i' = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F, cyclic.
 template <> struct DenseOde<MAGI_MODEL_L96> {
-    static constexpr int K = 1;
+    static constexpr int K = 1, KX = 1;
+    __device__ static void prepare(double*) {}
     template <class X> __device__ static double f(int d, X x, const double* th, int D) {
         const int p1 = (d + 1) % D, m1 = (d + D - 1) % D, m2 = (d + D - 2) % D;
         return (x(p1) - x(m2)) * x(m1) - x(d) + th[0];
@@ -75,9 +77,10 @@ __global__ void dense_e_kernel(const double* __restrict__ params, long long pitc
     constexpr int K = DenseOde<MODEL>::K;
     const int c = blockIdx.y;
     const double* xp = params + (size_t)c * pitch;
-    double th[K];
+    double th[DenseOde<MODEL>::KX];
 #pragma unroll
     for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    DenseOde<MODEL>::prepare(th);
     const size_t plane = (size_t)n * n_chains;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
@@ -123,9 +126,10 @@ __global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) 
         if (gp) for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = NAN;
         return;
     }
-    double th[K];
+    double th[DenseOde<MODEL>::KX];
 #pragma unroll
     for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    DenseOde<MODEL>::prepare(th);
     if (threadIdx.x == 0) sbad = 0;
     const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
     double gth[K];

@@ -40,6 +40,7 @@ extern "C" int magi_destroy(magi_handle* h) {
     free_dev(h->d_dense_work); free_dev(h->d_dense_ops);
     hmc_free(h);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < 3; ++i) if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);
     delete h;
     return MAGI_OK;
 }
@@ -127,7 +128,7 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
     if (!h->dense_mode) {
         size_t fsz = (size_t)4 * h->D * h->geom.NT * h->geom.NCH * 32;
         if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
-        banded_pick_config(h->D, h->K, h->geom.NT, h->smem_limit, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
+        banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
     }
     if (h->setup_mode != MAGI_SETUP_INJECT) {
         rc = run_device_setup(h);
@@ -203,7 +204,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
         cudaMemcpy(v.data(), d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < nblk * nwarp; ++i) { for (int j = 0; j < 8; ++j) s[j] += (double)v[i * 8 + j]; }
-        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: P1=%.0f sync=%.0f P2=%.0f sync=%.0f P3=%.0f sync|fine_pre=%.0f fine_dmma=%.0f fine_point=%.0f\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
+        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: A1=%.0f sync=%.0f A2=%.0f sync=%.0f (A2 fine: barrier=%.0f shift+loads=%.0f dmma=%.0f pointwise=%.0f)\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
                 s[0] / (nblk * nwarp), s[1] / (nblk * nwarp), s[2] / (nblk * nwarp), s[3] / (nblk * nwarp), s[4] / (nblk * nwarp), s[5] / (nblk * nwarp), s[6] / (nblk * nwarp), s[7] / (nblk * nwarp));
         cudaFree(d_dbg);
     }
@@ -233,6 +234,33 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     int rc = ensure_capacity(h, n_chains);
     if (rc) return rc;
     const size_t nb = sizeof(double) * (size_t)n_chains * h->P;
+    // Large batches: chunks over three streams so that the H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of
+    // chunk i-1 overlap (PCIe is full duplex; with pinned host buffers the call is bound by one direction of the link
+    // instead of H2D + kernel + D2H in sequence).  The banded kernel keeps its scratch in shared memory, so chunks are
+    // independent; other configurations take the single-stream path.
+    const int chunk_min = 1024;
+    if (n_chains >= 2 * chunk_min && !h->dense_mode && h->scratch_in_smem && h->tables_ready) {
+        for (int i = 0; i < 3; ++i)
+            if (!h->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        rc = refresh_fragtab(h, h->stream);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(h->stream), "stream sync");
+        int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
+        const int per = ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32;
+        int i = 0;
+        for (int c0 = 0; c0 < n_chains; c0 += per, ++i) {
+            const int nc = (n_chains - c0 < per) ? n_chains - c0 : per;
+            cudaStream_t st = h->pipe_streams[i % 3];
+            const size_t off = (size_t)c0 * h->P;
+            CK(cudaMemcpyAsync(h->d_params + off, params + off, sizeof(double) * (size_t)nc * h->P, cudaMemcpyHostToDevice, st), "H2D params");
+            rc = eval_dev(h, nc, h->d_params + off, h->P, h->d_ll + c0, grad ? h->d_grad + off : nullptr, st);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(ll + c0, h->d_ll + c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, st), "D2H ll");
+            if (grad) CK(cudaMemcpyAsync(grad + off, h->d_grad + off, sizeof(double) * (size_t)nc * h->P, cudaMemcpyDeviceToHost, st), "D2H grad");
+        }
+        for (int k = 0; k < 3; ++k) CK(cudaStreamSynchronize(h->pipe_streams[k]), "stream sync");
+        return MAGI_OK;
+    }
     CK(cudaMemcpyAsync(h->d_params, params, nb, cudaMemcpyHostToDevice, h->stream), "H2D params");
     rc = eval_dev(h, n_chains, h->d_params, h->P, h->d_ll, grad ? h->d_grad : nullptr, h->stream);
     if (rc) return rc;

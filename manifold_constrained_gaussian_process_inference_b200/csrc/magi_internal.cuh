@@ -30,6 +30,7 @@ struct magi_handle {
     double* d_dense_work = nullptr;
     size_t dense_work_cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};   // H2D / kernel / D2H overlap in the host-buffer batched call
     long long launches = 0;
     int smem_limit = 0, sm_count = 148;
     int G = 2, H = 1, DW = 1, scratch_in_smem = 1;

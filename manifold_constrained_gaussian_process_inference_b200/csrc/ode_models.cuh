@@ -4,7 +4,9 @@
 //   jx_col_sub(j, x, th, w, g)       g -= sum_p (df_p/dx_j) * w[p], p ascending -- the order the reference's
 //                                    dimension loop accumulates (src/likelihoods.jl:214-216)
 //   jth_row_sub(p, x, th, w, acc)    acc[q] -= (df_p/dth_q) * w for q < K        (src/likelihoods.jl:219-221)
-// x holds ALL D components (small-D models).  Divisions by loop-invariant parameters are hoisted by the compiler;
+// x holds ALL D components (small-D models).  th holds the K parameters followed by KX - K per-chain invariants filled by
+// prepare(th) ONCE per chain (an FP64 division is a ~30-instruction dependent chain on the FP64 pipe the DMMAs need; under
+// register pressure the compiler re-evaluates 1/c at every time point instead of hoisting it);
 // the only deliberate deviation from the reference's arithmetic is V^3/3.0 written as a multiplication by 1/3
 // (<= 1 ulp), because an FP64 division costs ~10 DFMA-pipe slots per time point.
 #pragma once
@@ -16,31 +18,36 @@ template <int MODEL> struct Ode;
 
 // ---- FitzHugh-Nagumo: src/ode_models.jl:39-47, 248-262, 274-299 ----
 template <> struct Ode<MAGI_MODEL_FN> {
-    static constexpr int D = 2, K = 3;
+    static constexpr int D = 2, K = 3, KX = 7;      // th[3] = 1/c, th[4] = -1/c, th[5] = -b/c, th[6] = 1/(c*c)
+    __device__ __forceinline__ static void prepare(double* th) {
+        const double b = th[1], c = th[2];
+        th[3] = 1.0 / c; th[4] = -1.0 / c; th[5] = -b / c; th[6] = 1.0 / (c * c);
+    }
     __device__ __forceinline__ static double f(int d, const double* x, const double* th) {
         const double V = x[0], R = x[1], a = th[0], b = th[1], c = th[2];
         if (d == 0) return c * (V - (V * V * V) * (1.0 / 3.0) + R);
-        return (-1.0 / c) * (V - a + b * R);
+        return th[4] * (V - a + b * R);                                   // (-1.0/c) * (V - a + b R)
     }
     __device__ __forceinline__ static void jx_col_sub(int j, const double* x, const double* th, const double* w, double& g) {
-        const double V = x[0], b = th[1], c = th[2];
-        if (j == 0) { g -= (c * (1.0 - V * V)) * w[0]; g -= (-1.0 / c) * w[1]; }
-        else        { g -= c * w[0];                   g -= (-b / c) * w[1]; }
+        const double V = x[0], c = th[2];
+        if (j == 0) { g -= (c * (1.0 - V * V)) * w[0]; g -= th[4] * w[1]; }
+        else        { g -= c * w[0];                   g -= th[5] * w[1]; }
     }
     __device__ __forceinline__ static void jth_row_sub(int p, const double* x, const double* th, double w, double* acc) {
-        const double V = x[0], R = x[1], a = th[0], b = th[1], c = th[2];
+        const double V = x[0], R = x[1], a = th[0], b = th[1];
         if (p == 0) { acc[2] -= (V - (V * V * V) * (1.0 / 3.0) + R) * w; }
         else {
-            acc[0] -= (1.0 / c) * w;
-            acc[1] -= (-R / c) * w;
-            acc[2] -= ((1.0 / (c * c)) * (V - a + b * R)) * w;
+            acc[0] -= th[3] * w;
+            acc[1] -= (-R * th[3]) * w;                                   // -R/c (<= 1 ulp from the reference's division)
+            acc[2] -= (th[6] * (V - a + b * R)) * w;
         }
     }
 };
 
 // ---- Hes1: src/ode_models.jl:60-70, 312-336, 349-378 ----
 template <> struct Ode<MAGI_MODEL_HES1> {
-    static constexpr int D = 3, K = 7;
+    static constexpr int D = 3, K = 7, KX = 7;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static double f(int d, const double* x, const double* p) {
         const double P = x[0], M = x[1], H = x[2];
         if (d == 0) return -p[0] * P * H + p[1] * M - p[2] * P;
@@ -70,7 +77,8 @@ template <> struct Ode<MAGI_MODEL_HES1> {
 
 // ---- Lotka-Volterra (not in the reference; BASELINE config 3): x' = a x - b x y, y' = d x y - g y ----
 template <> struct Ode<MAGI_MODEL_LV> {
-    static constexpr int D = 2, K = 4;
+    static constexpr int D = 2, K = 4, KX = 4;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static double f(int d, const double* x, const double* th) {
         if (d == 0) return th[0] * x[0] - th[1] * x[0] * x[1];
         return th[2] * x[0] * x[1] - th[3] * x[1];
@@ -88,7 +96,8 @@ template <> struct Ode<MAGI_MODEL_LV> {
 // ---- Hes1 in log coordinates: src/ode_models.jl:83-103 (+ fixed-parameter variants :116-165).
 // The reference ships no Jacobians for these; the ones below are derived and FD-checked in tests. ----
 template <int VARIANT> struct OdeHes1Log {   // 0: 7 params; 1: gamma fixed 0.3 (6 params); 2: f fixed 20 (6 params)
-    static constexpr int D = 3, K = (VARIANT == 0 ? 7 : 6);
+    static constexpr int D = 3, K = (VARIANT == 0 ? 7 : 6), KX = K;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static void unpack(const double* p, double* q) {
         q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = p[3]; q[4] = p[4];
         if (VARIANT == 0) { q[5] = p[5]; q[6] = p[6]; }
@@ -139,7 +148,8 @@ template <> struct Ode<MAGI_MODEL_HES1LOG_FIXF> : OdeHes1Log<2> {};
 
 // ---- HIV in log coordinates: src/ode_models.jl:178-207 (Jacobians derived) ----
 template <> struct Ode<MAGI_MODEL_HIV> {
-    static constexpr int D = 4, K = 9;
+    static constexpr int D = 4, K = 9, KX = 9;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static double f(int d, const double* x, const double* p) {
         const double T = exp(x[0]), Tm = exp(x[1]), Tw = exp(x[2]), Tmw = exp(x[3]);
         const double sf = 1e-6;
@@ -175,7 +185,8 @@ template <> struct Ode<MAGI_MODEL_HIV> {
 
 // ---- protein transduction: src/ode_models.jl:219-233 (Jacobians derived) ----
 template <> struct Ode<MAGI_MODEL_PTRANS> {
-    static constexpr int D = 5, K = 6;
+    static constexpr int D = 5, K = 6, KX = 6;
+    __device__ __forceinline__ static void prepare(double*) {}
     __device__ __forceinline__ static double f(int d, const double* x, const double* p) {
         const double S = x[0], R = x[2], RS = x[3], RPP = x[4];
         if (d == 0) return -p[0] * S - p[1] * S * R + p[2] * RS;

@@ -153,3 +153,18 @@ def test_lorenz96_dense_path(pkg):
     ll, g = tg.logdensity_and_gradient_batched(params)
     ll_ref, g_ref = H.oracle_batched(prob)
     H.assert_parity(ll, g, ll_ref, g_ref, "lorenz96")
+
+
+def test_pipelined_host_call_matches_single_stream(pkg):
+    """Batches >= 2048 chains go through the chunked H2D / kernel / D2H pipeline: results must be bit-identical to
+    evaluating the same chains in small calls."""
+    prob = H.make_problem(n=41, T=8.0, b=6, n_chains=8, seed=21)
+    tg = H.cuda_target(pkg, prob)
+    rng = np.random.default_rng(0)
+    params = np.repeat(prob["params"], 400, axis=0) + 1e-3 * rng.normal(size=(3200, prob["params"].shape[1]))
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    ll2 = np.concatenate([tg.logdensity_and_gradient_batched(params[i:i + 800])[0] for i in range(0, 3200, 800)])
+    g2 = np.concatenate([tg.logdensity_and_gradient_batched(params[i:i + 800])[1] for i in range(0, 3200, 800)])
+    assert np.array_equal(ll, ll2) and np.array_equal(g, g2)
+    ll_ref, g_ref = H.oracle_batched(prob, params[::457])
+    H.assert_parity(ll[::457], g[::457], ll_ref, g_ref, "pipelined")
