@@ -94,30 +94,29 @@ size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)G *
 // fragment ring, two time segments when the time axis is long enough to amortise the halo.
 void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
     const int RED = 4 + K, NCH = 2 * HB + 2;
-    DW = D < 8 ? D : 8;
+    DW = D;
     H = 1;
     int gmax = 4;
     if (const char* e = getenv("MAGI_FORCE_G")) gmax = atoi(e);
     const bool force_global = getenv("MAGI_FORCE_GLOBAL_SCRATCH") != nullptr;
-    const int max_warps = (D * 128 > 512 ? 512 : D * 128) / 32;
-    auto ring_bytes_for = [&](int) { return ((size_t)DW * 2 * 4 * NCH * 32 + 16) * sizeof(double); };   // rings + mbarriers
-    // As many chain-groups per block as possible first (they share the fragment ring and fill the SM's schedulers); for
-    // long time axes the Ke scratch of four groups does not fit shared memory and goes to global memory (L2-resident):
-    // measured on LV n=1281: G=4 with L2 scratch 0.27 ms vs G=1 with shared-memory scratch 0.45 ms.
+    // rings [D][2 stages][4 blocks] + exchange [G*D tasks][2 stages][12 slots][32 lanes] + mbarriers
+    auto fixed_bytes = [&](int g) { return ((size_t)D * 2 * 4 * NCH * 32 + (size_t)g * D * 2 * 12 * 32 + 2 * D + 4 * g * D) * sizeof(double); };
+    // As many chain-groups per block as fit 16 warps (2 warps per task); for long time axes the Ke scratch of that many
+    // groups does not fit shared memory and goes to global memory (L2-resident): on LV n=1281 G=4 with L2 scratch ran in
+    // 0.27 ms against 0.45 ms for G=1 with shared-memory scratch.
     for (int g = gmax; g >= 1; --g) {
-        if (g * DW > max_warps) continue;
-        for (int pass = 0; pass < 2; ++pass) {          // pass 0: Ke scratch in shared memory; pass 1: in global memory (L2)
+        if (2 * g * D > 16) continue;
+        for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0 && force_global) continue;
             size_t red = (size_t)g * 8 * D * RED * sizeof(double);
             size_t scr = pass == 0 ? banded_scratch_doubles_per_cta(g, D, NT) * sizeof(double) : 0;
-            size_t tot = scr + ring_bytes_for(g) + red;
+            size_t tot = scr + fixed_bytes(g) + red;
             if (tot <= (size_t)smem_limit) { G = g; scratch_in_smem = (pass == 0); smem_bytes = tot; return; }
         }
     }
     G = 1; scratch_in_smem = 0;
-    smem_bytes = ring_bytes_for(1) + (size_t)8 * D * RED * sizeof(double);
+    smem_bytes = fixed_bytes(1) + (size_t)8 * D * RED * sizeof(double);
 }
-
 
 // one translation unit per model instantiates the kernels (banded_inst_*.cu), so they compile in parallel
 #define MAGI_DECL_MODEL(M) cudaError_t launch_banded_model_##M(const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st);

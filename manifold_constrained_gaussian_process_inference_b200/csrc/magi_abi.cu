@@ -194,7 +194,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     a.dbg = nullptr;
     static const bool dbg_clocks = getenv("MAGI_DBG_CLOCKS") != nullptr;
     long long* d_dbg = nullptr;
-    const int nblk = (n_chains + h->G * 8 - 1) / (h->G * 8), nwarp = h->G * h->DW * h->H;
+    const int nblk = (n_chains + h->G * 8 - 1) / (h->G * 8), nwarp = h->G * h->DW;
     if (dbg_clocks) { cudaMalloc(&d_dbg, sizeof(long long) * 8 * nblk * nwarp); cudaMemset(d_dbg, 0, sizeof(long long) * 8 * nblk * nwarp); a.dbg = d_dbg; }
     CK(launch_banded_cfg(h->model, a, h->geom.HB, h->DW, h->smem_bytes, st), "banded_logpost_kernel launch");
     h->launches++;

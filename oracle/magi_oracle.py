@@ -618,6 +618,9 @@ def log_likelihood_and_gradient_banded(xlatent, theta, sigma, yobs, covs, model:
     gX = np.zeros((n, D), dtype=X.dtype)
     gth = np.zeros(k, dtype=X.dtype)
     gsig = np.zeros(D, dtype=X.dtype)
+    if model.dfdx is None or model.dfdtheta is None:
+        # the reference ships no Jacobians for this model (src/ode_models.jl:83-233): value only, gradient left NaN
+        return ll, np.full(n * D + k + D, np.nan, dtype=X.dtype)
     Jx = model.dfdx(X, th)            # (n, D, D); the reference re-evaluates it D times (:199-209) -- same values
     Jp = model.dfdtheta(X, th)        # (n, D, k)
     for d in range(D):                                                    # :168-247

@@ -168,3 +168,43 @@ def test_pipelined_host_call_matches_single_stream(pkg):
     assert np.array_equal(ll, ll2) and np.array_equal(g, g2)
     ll_ref, g_ref = H.oracle_batched(prob, params[::457])
     H.assert_parity(ll[::457], g[::457], ll_ref, g_ref, "pipelined")
+
+
+@pytest.mark.parametrize("name,mid,D,k", [("hes1log", mo.MODEL_HES1LOG, 3, 7), ("hes1log_fixg", mo.MODEL_HES1LOG_FIXG, 3, 6),
+                                          ("hes1log_fixf", mo.MODEL_HES1LOG_FIXF, 3, 6), ("hiv", mo.MODEL_HIV, 4, 9), ("ptrans", mo.MODEL_PTRANS, 5, 6)])
+def test_models_without_reference_jacobians(pkg, name, mid, D, k):
+    """Hes1-log (3 variants), HIV and protein-transduction have a right-hand side in the reference (src/ode_models.jl:83-233)
+    but no Jacobians: the log density must match the oracle, and the device gradient (derived Jacobians) must match
+    central finite differences of the device log density."""
+    rng = np.random.default_rng(40 + mid)
+    n, b, nc = 24, 5, 3
+    t = np.linspace(0.0, 4.0, n)
+    covs = [mo.calculate_gp_covariances(mo.MATERN52, [1.0 + 0.2 * d, 1.0 + 0.1 * d], t, b, jitter=1e-6) for d in range(D)]
+    base = 0.3 * np.sin(t[:, None] + np.arange(D)[None, :]) + (1.0 if name == "ptrans" else 0.2)
+    Y = np.full((n, D), np.nan); Y[::2] = base[::2] + 0.05 * rng.normal(size=base[::2].shape)
+    tgt = mo.make_target(Y, covs, mid, np.full(D, 0.1), (1.0, 1.0, 1.0), False)
+    th0 = (np.array([10.0, 1.0, 2.0, 3.0, 4.0, 5.0, 1.0, 1.0, 1.0]) if name == "hiv" else 0.3 + 0.1 * np.arange(k))
+    params = np.stack([np.concatenate([(base + 0.05 * rng.normal(size=base.shape)).reshape(-1, order="F"), th0 * np.exp(0.05 * rng.normal(size=k)),
+                                       np.log(0.1) + 0.05 * rng.normal(size=D)]) for _ in range(nc)])
+    prob = dict(target=tgt, params=params, covs=covs)
+    tg = H.cuda_target(pkg, prob)
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    ll_ref = np.array([mo.logdensity(tgt, p) for p in params])
+    assert np.all(np.isfinite(ll)) and np.all(np.isfinite(g))
+    assert np.max(np.abs(ll - ll_ref) / np.abs(ll_ref)) <= H.LL_RTOL
+    P = params.shape[1]
+    idx = rng.choice(P, size=24, replace=False)
+    idx = np.unique(np.concatenate([idx, np.arange(n * D, P)]))             # always include theta and log sigma
+    p0 = params[0]
+    pert = []
+    hs = []
+    for i in idx:
+        h = 1e-5 * max(1.0, abs(p0[i]))
+        for sgn in (-2, -1, 1, 2):
+            q = p0.copy(); q[i] += sgn * h; pert.append(q)
+        hs.append(h)
+    lls, _ = tg.logdensity_and_gradient_batched(np.array(pert), want_grad=False)
+    lls = lls.reshape(len(idx), 4)
+    fd = (lls[:, 0] - 8 * lls[:, 1] + 8 * lls[:, 2] - lls[:, 3]) / (12 * np.array(hs))
+    scale = np.maximum(np.abs(fd), 1e-3 * np.abs(g[0]).max())
+    assert np.max(np.abs(fd - g[0][idx]) / scale) < 1e-5, (name, np.max(np.abs(fd - g[0][idx]) / scale))
