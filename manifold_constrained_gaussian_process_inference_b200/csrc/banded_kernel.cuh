@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     M::prepare(th);
     const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+    long long wbar = 0, wp2c = 0, wfull = 0, wc2p = 0;     // MAGI_DBG_WAITS: cycles spent in each kind of wait (A2 only)
     if (a.dbg) tk0 = clock64();
 
     auto stage_blocks = [&](unsigned use, const double* s0, const double* s1, const double* s2, const double* s3) {
@@ -200,12 +201,19 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             named_barrier(1 + d, ring_threads);
             stage_step(0, ring_use);
             for (int u = 0; u <= uA1_end; ++u, ++ring_use, ++xuse) {
+#ifdef MAGI_DBG_WAITS1
+                long long w0 = clock64();
+#endif
                 named_barrier(1 + d, ring_threads);          // all DMMA warps of this dimension finished step u-1
+#ifdef MAGI_DBG_WAITS1
+                long long w1 = clock64(); wbar += w1 - w0;
+#endif
                 stage_step(u + 1, ring_use + 1);
                 double* xs = xch + (size_t)(xuse & 1) * XS * 32;
                 double fin[8];                               // e tiles of step u-2 (4) and x feed of this step (4)
-#ifndef MAGI_ABL_NOWAIT
                 if (xuse >= 2) mbar_wait(p2c + (xuse & 1), ((xuse - 2) >> 1) & 1);
+#ifdef MAGI_DBG_WAITS1
+                long long w2 = clock64(); wp2c += w2 - w1;
 #endif
                 if (u >= 2) {
 #pragma unroll
@@ -219,7 +227,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; ew[i] = ew[i + 4]; }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { ew[W2 - 4 + i] = fin[i]; xw[W2 - 4 + i] = fin[4 + i]; }
+#ifdef MAGI_DBG_WAITS1
+                long long w3 = clock64();
+#endif
                 mbar_wait(full + (ring_use & 1), (ring_use >> 1) & 1);
+#ifdef MAGI_DBG_WAITS1
+                wfull += clock64() - w3;
+#endif
                 const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)(ring_use & 1) * 4 * BLK) + lane;
                 const int Ja = 2 * u - LAGT, Jb = 2 * u - 4 - 2 * LAGT;
                 const bool va = tile_ok(Ja) || tile_ok(Ja + 1), vb = tile_ok(Jb) || tile_ok(Jb + 1);
@@ -288,12 +302,19 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             named_barrier(1 + d, ring_threads);
             stage_step(0, ring_use);
             for (int u = 0; u <= uA2_end; ++u, ++ring_use, ++xuse) {
+#ifdef MAGI_DBG_WAITS
+                long long w0 = clock64();
+#endif
                 named_barrier(1 + d, ring_threads);
+#ifdef MAGI_DBG_WAITS
+                long long w1 = clock64(); wbar += w1 - w0;
+#endif
                 stage_step(u + 1, ring_use + 1);
                 double* xs = xch + (size_t)(xuse & 1) * XS * 32;
                 double feed[4];
-#ifndef MAGI_ABL_NOWAIT
                 if (xuse >= 2) mbar_wait(p2c + (xuse & 1), ((xuse - 2) >> 1) & 1);     // P consumed this stage two steps ago
+#ifdef MAGI_DBG_WAITS
+                long long w2 = clock64(); wp2c += w2 - w1;
 #endif
                 if (u >= 2) {
 #pragma unroll
@@ -309,7 +330,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     kw[W2 - 4 + 2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64] : 0.0;
                     kw[W2 - 3 + 2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64 + 32] : 0.0;
                 }
+#ifdef MAGI_DBG_WAITS
+                long long w3 = clock64();
+#endif
                 mbar_wait(full + (ring_use & 1), (ring_use >> 1) & 1);
+#ifdef MAGI_DBG_WAITS
+                wfull += clock64() - w3;
+#endif
                 const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)(ring_use & 1) * 4 * BLK) + lane;
                 const int Jc = 2 * u - LAGT;
                 double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -361,7 +388,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 for (int i = 0; i < 4; ++i) feed[i] = nfeed[i];
                 if (u < uA1_end) load_a1(u + 1, nxa, nfeed);
                 double* xs = xch + (size_t)(xuse & 1) * XS * 32;
+#ifdef MAGI_DBG_WAITS1
+                long long w0 = clock64();
+#endif
                 mbar_wait(c2p + (xuse & 1), (xuse >> 1) & 1);
+#ifdef MAGI_DBG_WAITS1
+                wc2p += clock64() - w0;
+#endif
                 const double mm[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}};
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
@@ -432,7 +465,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 }
             }
             double* xs = xch + (size_t)(xuse & 1) * XS * 32;
+#ifdef MAGI_DBG_WAITS
+            long long w0 = clock64();
+#endif
             mbar_wait(c2p + (xuse & 1), (xuse >> 1) & 1);
+#ifdef MAGI_DBG_WAITS
+            wc2p += clock64() - w0;
+#endif
             const double cxv[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}}, mtv[2][2] = {{xs[128], xs[160]}, {xs[192], xs[224]}};
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
@@ -481,9 +520,10 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     if (role == 0) dispatch_dim<D>(d_rt, c_warp);
     else dispatch_dim<D>(d_rt, p_warp);
     __syncthreads();
-    if (a.dbg && lane == 0 && role == 0) {
+    if (a.dbg && lane == 0) {
         long long* o = a.dbg + ((size_t)blockIdx.x * ntask + task) * 8;
-        o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tk3 - tk2; o[3] = clock64() - tk3; o[4] = 0; o[5] = 0; o[6] = 0; o[7] = 0;
+        if (role == 0) { o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tk3 - tk2; o[3] = clock64() - tk3; o[4] = wbar; o[5] = wp2c; o[6] = wfull; }
+        else o[7] = wc2p;
     }
 
     // ---------------- final: one thread per chain ----------------

@@ -204,7 +204,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
         cudaMemcpy(v.data(), d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < nblk * nwarp; ++i) { for (int j = 0; j < 8; ++j) s[j] += (double)v[i * 8 + j]; }
-        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: A1=%.0f sync=%.0f A2=%.0f sync=%.0f (A2 fine: barrier=%.0f shift+loads=%.0f dmma=%.0f pointwise=%.0f)\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
+        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: A1=%.0f sync=%.0f A2=%.0f sync=%.0f (A2 waits: C ring barrier=%.0f, C for P=%.0f, C for TMA=%.0f, P for C=%.0f)\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
                 s[0] / (nblk * nwarp), s[1] / (nblk * nwarp), s[2] / (nblk * nwarp), s[3] / (nblk * nwarp), s[4] / (nblk * nwarp), s[5] / (nblk * nwarp), s[6] / (nblk * nwarp), s[7] / (nblk * nwarp));
         cudaFree(d_dbg);
     }
