@@ -1,27 +1,27 @@
-// K1: fused banded log-posterior + gradient on FP64 tensor cores (DMMA.8x8x4), and K6: band -> fragment tables.
+// K1: fused banded log-posterior + gradient on FP64 tensor cores (DMMA.8x8x4).
 //
 // Replaces, for a batch of independent chains, the reference's
 //   log_likelihood_and_gradient_banded          src/likelihoods.jl:43-257
 //   LogDensityProblems.logdensity_and_gradient  src/logdensityproblems_interface.jl:176-267
 //
 // Formulation.  For every dimension d the four band products (m~ x, K~ e, C~ x, m~^T Ke; likelihoods.jl:129,132,133,192)
-// are written as (chains x time) = (chains x time) . (band table) products: 8 chains form the M extent of a
-// DMMA.8x8x4, 8 output times its N extent, and the contraction runs over 4-time chunks.  A warp owns one
-// (chain-group, dimension) task and sweeps the time axis once per phase; the operand (x, e, Ke) lives in a register
-// window of WN chunks that slides by one 8-time tile per step, so every state value is read from memory once per
-// sweep and the only per-DMMA load is the 256-byte table fragment (shared by every chain on the GPU: L1/L2 hits).
-// The time->slot permutation (lane (gid,q) owns times 8J+q and 8J+q+4 of tile J) makes the C fragment of one
-// product directly usable as the A fragment of the next, so x -> e -> Ke never leaves registers.
+// are written as (chains x time) = (chains x time) . (band table) products: 8 chains form the M extent of a DMMA.8x8x4,
+// 8 output times its N extent, and the contraction runs over 4-time chunks.  The operand (x, e, Ke) lives in a register
+// window that slides along the time axis, so every state value enters the tensor pipe from registers and the only
+// per-DMMA load is the table fragment (staged once per block in shared memory by TMA).  The time->slot permutation
+// (lane (gid,q) owns times 8J+q and 8J+q+4 of tile J) makes the C fragment of one product directly usable as the A
+// fragment of the next.
 //
-//   phase A1 (per task):  mx = m~ x_d;  e = f_d(x, theta) - mx;  Ke = K~ e  -> Ke to scratch; sum e.Ke
-//   phase A2 (per task):  Cx = C~ x_d;  mt = m~^T Ke_d;  pointwise gradient incl. the ODE Jacobian terms, which need
-//                         Ke of ALL dimensions at the same time point (hence the block-wide barrier in between)
-//   final   (per chain):  log-likelihood assembly in the reference's term order, sigma gradient, log-sigma
-//                         transform and the per-chain -Inf / zero-gradient guards.
+//   phase A1:  mx = m~ x_d;  e = f_d(x, theta) - mx;  Ke = K~ e  -> Ke scratch; sum e.Ke
+//   phase A2:  Cx = C~ x_d;  mt = m~^T Ke_d;  pointwise gradient incl. the ODE Jacobian terms, which need Ke of ALL
+//              dimensions at the same time point (hence the block-wide barrier in between)
+//   final (per chain):  log-likelihood assembly in the reference's term order, sigma gradient, log-sigma transform and the
+//              per-chain -Inf / zero-gradient guards (interface.jl:179-264).
+// Warp roles, exchange protocol and the measured behaviour: see the comment above the kernel and DESIGN.md section 4.
+#pragma once
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
-#pragma once
 #include "magi_common.cuh"
 #include "ode_models.cuh"
 
@@ -60,19 +60,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// ---- async-copy helpers ----
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gsrc) : "memory");
-}
-// 8-byte async copy of one state value into this lane's private staging slot; zero-fills when !ok (src-size 0)
-__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gsrc, bool ok) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = ok ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
 
 // One block = G chain-groups (8 chains each) x DW dimension slots, one warp per (group, dim) task, sweeping the time axis
