@@ -130,6 +130,13 @@ int magi_gp_covariances(int kernel_id, const double* phi, const double* tvec, in
                         double* Cdoubleprime, double* mphi, double* Kphi, double* Kinv, double* CinvBand,
                         double* mphiBand, double* KinvBand, int* repaired);
 
+/* GP hyper-parameter initialisation objective: negative log marginal likelihood of
+ * Initialization.negative_log_marginal_likelihood (src/initialization.jl:72-176) for n_cand candidate vectors
+ * (log variance, log lengthscale, log sigma) on the n finite observations (t, y) of one dimension.  Invalid parameters or
+ * non-finite results give +Inf, as in the reference. */
+int magi_gp_nlml_batched(int kernel_id, int n, const double* t, const double* y, double jitter, int n_cand,
+                         const double* log_params /* 3 x n_cand */, double* out /* n_cand */, int device);
+
 /* ---- on-device batched HMC: the sampler loop of run_nuts_sampler (src/samplers.jl:114-194:
  * diagonal Euclidean metric, leapfrog, Stan-style step-size and metric adaptation) with the chain state resident in HBM.
  * Static trajectories of n_leapfrog steps; every leapfrog step is one evaluation of the hot path for every chain.

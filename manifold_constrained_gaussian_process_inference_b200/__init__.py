@@ -9,7 +9,7 @@ from .ode_models import OdeSystem, get_ode_system, fn_system, hes1_system, lv_sy
 from .gaussian_process import GPCov, calculate_gp_covariances, mat2band
 from .samplers import run_hmc_sampler
 from .solver import solve_magi
-from . import diagnostics, distributed
+from . import diagnostics, distributed, initialization
 from .target import MagiTarget, dimension, capabilities, logdensity, logdensity_and_gradient, LogDensityOrder
 
 __all__ = [

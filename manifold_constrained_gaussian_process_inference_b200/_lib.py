@@ -41,7 +41,7 @@ EXPORTED = [
     "magi_last_error", "magi_version", "magi_create", "magi_destroy", "magi_dimension", "magi_capabilities_order",
     "magi_logdensity", "magi_logdensity_and_gradient", "magi_logdensity_and_gradient_batched",
     "magi_logdensity_and_gradient_batched_dev", "magi_get_matrix", "magi_set_band_tables", "magi_setup_status",
-    "magi_launch_count", "magi_gp_covariances", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
+    "magi_launch_count", "magi_gp_covariances", "magi_gp_nlml_batched", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
     "magi_hmc_get_state", "magi_hmc_get_draws", "magi_hmc_draws_dev", "magi_hmc_get_stats", "magi_hmc_grad_evals",
 ]
 
@@ -82,6 +82,8 @@ def _optional(L):
     vp, ci, dp = ctypes.c_void_p, ctypes.c_int, c_double_p
     if hasattr(L, "magi_gp_covariances"):
         L.magi_gp_covariances.argtypes = [ci, dp, dp, ci, ci, ctypes.c_double, ci, ci, ci, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, c_int_p]
+    if hasattr(L, "magi_gp_nlml_batched"):
+        L.magi_gp_nlml_batched.argtypes = [ci, ci, dp, dp, ctypes.c_double, ci, dp, dp, ci]
     if hasattr(L, "magi_hmc_init"):
         ll = ctypes.c_longlong
         L.magi_hmc_init.argtypes = [vp, ci, dp, ctypes.c_ulonglong, ctypes.c_double, ll]

@@ -7,13 +7,14 @@ bounds-based θ init (:412-453), band clamp (:459), parameter vector layout [vec
 (:578-581) and the shape of the result (θ, σ, lp; :633-771).  New keys: :nChains (independent chains, default 1024),
 :nLeapfrog (static trajectory length), :setupMode, :seed, :device.
 
-Out of scope here: the Nelder-Mead GP hyper-parameter initialisation
-(src/initialization.jl); ``config['phi']`` is therefore required, and ``config['sigma']`` (fixed) or
-``config['sigmaInit']`` (starting value when σ is sampled)."""
+When ``config['phi']`` and/or ``config['sigma']`` are absent they are estimated per dimension by minimising the GP negative log
+marginal likelihood (src/MagiJl.jl:254-330 -> src/initialization.jl), objective on the GPU, Nelder-Mead on the host
+(``initialization.py``); ``config['sigmaInit']`` overrides the estimated starting σ."""
 from __future__ import annotations
 
 import numpy as np
 
+from . import initialization
 from .ode_models import OdeSystem
 from .samplers import run_hmc_sampler
 from .target import MagiTarget
@@ -83,14 +84,35 @@ def solve_magi(y_obs, t_obs, ode_system: OdeSystem, config=None, initial_params=
     delta = float(get("targetAcceptRatio", 0.8))
     phi = get("phi", None)
     sigma = get("sigma", None)
-    if phi is None:
-        raise NotImplementedError("config['phi'] (2 x D GP hyper-parameters) is required: the Nelder-Mead initialisation of "
-                                  "src/initialization.jl is outside the accelerated path (SURVEY.md section 8(f) rank 3)")
+    sigma_is_fixed = (sigma is not None) and (phi is not None)               # :224
+    device = int(get("device", 0))
+    sigma_est = None
+    if phi is None or sigma is None:                                        # :254-330: Option A, estimate per dimension
+        phi_est = np.zeros((2, D))
+        sigma_est = np.zeros(D)
+        for d in range(D):
+            x0 = initialization.initial_guess(y[:, d], t)
+            if phi is not None:
+                x0[:2] = np.log(np.asarray(phi, dtype=np.float64).reshape(2, D)[:, d])
+            try:
+                opt = initialization.optimize_gp_hyperparameters(y[:, d], t, kernel, x0, jitter=jitter,
+                                                                 iterations=int(get("gpOptimIterations", 100)),
+                                                                 g_tol=float(get("gpOptimGTol", 1e-8)), device=device)
+            except Exception:                                               # :313-317 fall back to the initial guess
+                opt = np.exp(x0)
+            phi_est[:, d] = opt[:2]
+            sigma_est[d] = max(opt[2], 1e-8)                                # :326
+        if phi is None:
+            phi = phi_est
     phi = np.asarray(phi, dtype=np.float64).reshape(2, D)
     if np.any(~np.isfinite(phi)) or np.any(phi <= 0):
         raise ValueError("Invalid GP hyperparameters: variance and lengthscale must be finite and > 0")   # :469-472
-    sigma_is_fixed = sigma is not None                                     # :224 (phi is always given here)
-    sigma_init = np.asarray(sigma if sigma is not None else get("sigmaInit", np.full(D, 0.1 * np.nanstd(y))), dtype=np.float64)
+    if sigma is not None:
+        sigma_init = np.asarray(sigma, dtype=np.float64)
+    elif get("sigmaInit", None) is not None:
+        sigma_init = np.asarray(get("sigmaInit", None), dtype=np.float64)
+    else:
+        sigma_init = sigma_est
     n_chains = int(get("nChains", 1024))
     n_leap = int(get("nLeapfrog", 20))
     if kernel not in ("matern52", "rbf"):
@@ -102,7 +124,7 @@ def solve_magi(y_obs, t_obs, ode_system: OdeSystem, config=None, initial_params=
     th_init = initial_theta(ode_system) if th_init is None else np.clip(np.asarray(th_init, dtype=np.float64), ode_system.thetaLowerBound, ode_system.thetaUpperBound)
     target = MagiTarget.from_config(y, t, phi, ode_system, sigma_init, prior_temperature=beta, sigma_is_fixed=sigma_is_fixed,
                                     kernel=kernel, bandsize=band, jitter=jitter, setup_mode=get("setupMode", "reference_order"),
-                                    device=int(get("device", 0)), max_chains=n_chains)
+                                    device=device, max_chains=n_chains)
     P = target.dimension()
     if initial_params is None:
         parts = [x_init.reshape(-1, order="F"), th_init]

@@ -759,3 +759,27 @@ def make_target(yobs, covs, model_id, sigma_init, prior_temperature, sigma_is_fi
     return MagiTarget(yobs=yobs, gp_cov_all_dims=covs, model=model, sigma_init=np.asarray(sigma_init, dtype=dtype),
                       prior_temperature=tuple(prior_temperature), n_times=n, n_dims=D,
                       n_params_ode=model.n_params, sigma_is_fixed=bool(sigma_is_fixed), dtype=dtype)
+
+
+# --------------------------------------------------------------------------
+# GP hyper-parameter initialisation objective (src/initialization.jl:72-176)
+# --------------------------------------------------------------------------
+
+def negative_log_marginal_likelihood(log_params, y_obs_dim, t_obs, kernel: int, jitter: float = 1e-6):
+    """0.5 (log|K_phi + (sigma^2 + jitter) I| + y^T (.)^-1 y + N log 2 pi) on the non-NaN observations; Inf for invalid
+    parameters, no data or a non-finite result."""
+    variance, lengthscale, sigma = (float(np.exp(v)) for v in log_params)
+    if not all(np.isfinite([variance, lengthscale, sigma])) or min(variance, lengthscale, sigma) <= 0:
+        return np.inf
+    y = np.asarray(y_obs_dim, dtype=np.float64)
+    ok = ~np.isnan(y)
+    if not ok.any():
+        return np.inf
+    ys, ts = y[ok], np.asarray(t_obs, dtype=np.float64)[ok]
+    n = ys.shape[0]
+    K = kernel_matrix(kernel, ts, variance, lengthscale) + (sigma * sigma + jitter) * np.eye(n)     # :128
+    L, _ = positive_cholesky(K)                                                                  # :135
+    logdet = 2.0 * np.sum(np.log(np.diag(L)))                                                    # :138
+    z = _solve_lower(L, ys)
+    v = 0.5 * (logdet + float(z @ z) + n * np.log(2.0 * np.pi))                                  # :150
+    return v if np.isfinite(v) else np.inf

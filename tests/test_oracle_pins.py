@@ -230,3 +230,19 @@ def test_float64_envelope_against_long_double():
     assert abs(float(lll) - ll) / abs(ll) < 1e-12
     scale = np.maximum(np.abs(g), 1e-3 * np.abs(g).max())
     assert np.max(np.abs(np.asarray(gl, dtype=np.float64) - g) / scale) < 1e-11
+
+
+def test_nlml_restatement_against_direct_formula():
+    """src/initialization.jl:72-176: 0.5 (log|K + (s^2 + jitter) I| + y^T (.)^-1 y + N log 2 pi) on the non-NaN observations."""
+    rng = np.random.default_rng(1)
+    t = np.linspace(0.0, 10.0, 30)
+    y = np.sin(t) + 0.1 * rng.normal(size=30)
+    y[[3, 11]] = np.nan
+    lp = np.log([1.3, 0.9, 0.2])
+    ok = ~np.isnan(y)
+    K = mo.kernel_matrix(mo.MATERN52, t[ok], 1.3, 0.9) + (0.2 ** 2 + 1e-6) * np.eye(ok.sum())
+    sign, logdet = np.linalg.slogdet(K)
+    direct = 0.5 * (logdet + y[ok] @ np.linalg.solve(K, y[ok]) + ok.sum() * np.log(2 * np.pi))
+    assert np.isclose(mo.negative_log_marginal_likelihood(lp, y, t, mo.MATERN52, 1e-6), direct, rtol=1e-12)
+    assert mo.negative_log_marginal_likelihood(np.array([np.inf, 0.0, 0.0]), y, t, mo.MATERN52) == np.inf
+    assert mo.negative_log_marginal_likelihood(lp, np.full(30, np.nan), t, mo.MATERN52) == np.inf
