@@ -27,31 +27,39 @@
 namespace magi {
 
 // ------------------------------------------------------------------------------------------------------------
-// K6: fragment tables.  fragtab[view][d][J][hh/2][lane][hh&1] (chunk pairs interleaved per lane: one 16-byte load fetches
-// the fragments of chunks hh and hh+1), lane = 4*gid + q holds the B-operand entry
+// K6: fragment tables.  fragtab[view][d][pair p][hh][lane][tt]: pair p holds the tiles J = 2p - off + tt, tt = 0, 1
+// (off = LAGT & 1 for the views m~, C~, m~^T, whose sweep runs LAGT tiles behind the window head; 0 for K~), interleaved per
+// lane so that one 16-byte load fetches chunk hh of BOTH tiles -- the two DMMAs it feeds belong to different accumulate
+// chains.  lane = 4*gid + q holds the B-operand entry
 //   T[in = 4*(2J - HB + hh) + q][out = 8J + (gid>>1) + 4*(gid&1)]
 // with T[in][out] = A[out][in] for y = A x (views 0: m~, 1: C~, 2: K~) and T[in][out] = m~[in][out] for view 3 (m~^T).
 // Band rule |in - out| <= b as mat2band (gaussian_process.jl:70-74, 358-360).  Input tables are diagonal-major.
 // ------------------------------------------------------------------------------------------------------------
+size_t fragtab_doubles(int n, int b, int D) {
+    BandGeom g = band_geom(n, b);
+    return (size_t)4 * D * (g.NT / 2 + 1) * g.NCH * 64;
+}
+
 __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const double* __restrict__ band_mphi,
                                      const double* __restrict__ band_kinv, double* __restrict__ fragtab,
-                                     int n, int b, int D, int HB, int NCH, int NT) {
-    const size_t per_view = (size_t)D * NT * NCH * 32;
+                                     int n, int b, int D, int HB, int NCH, int NT, int LAGT) {
+    const int NP = NT / 2 + 1;
+    const size_t per_view = (size_t)D * NP * NCH * 64;
     const size_t total = 4 * per_view;
     const size_t tab = (size_t)(2 * b + 1) * n;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int within = (int)(idx % ((size_t)NCH * 32));       // position inside the (view, d, J) block
-        size_t r = idx / ((size_t)NCH * 32);
-        const int hh = 2 * (within >> 6) + (within & 1);
-        const int lane = (within >> 1) & 31;
-        int J = (int)(r % NT); r /= NT;
+        const int within = (int)(idx % ((size_t)NCH * 64));       // position inside the (view, d, pair) block
+        size_t r = idx / ((size_t)NCH * 64);
+        const int tt = within & 1, lane = (within >> 1) & 31, hh = within >> 6;
+        int p = (int)(r % NP); r /= NP;
         int d = (int)(r % D);
         int view = (int)(r / D);
+        const int J = 2 * p - (view == 2 ? 0 : (LAGT & 1)) + tt;
         int gid = lane >> 2, q = lane & 3;
         int o = 8 * J + (gid >> 1) + 4 * (gid & 1);
         int i = 4 * (2 * J - HB + hh) + q;
         double v = 0.0;
-        if (o < n && i >= 0 && i < n && abs(i - o) <= b) {
+        if (J >= 0 && J < NT && o < n && i >= 0 && i < n && abs(i - o) <= b) {
             const double* src = (view == 1) ? band_cinv : (view == 2 ? band_kinv : band_mphi);
             src += (size_t)d * tab;
             v = (view == 3) ? src[(size_t)(b + (o - i)) * n + i] : src[(size_t)(b + (i - o)) * n + o];
@@ -63,10 +71,10 @@ __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const
 cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
                                  int n, int b, int D, cudaStream_t st) {
     BandGeom g = band_geom(n, b);
-    size_t total = (size_t)4 * D * g.NT * g.NCH * 32;
+    size_t total = fragtab_doubles(n, b, D);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT);
+    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT, g.LAGT);
     return cudaGetLastError();
 }
 
@@ -99,8 +107,10 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int& G, in
     int gmax = 4;
     if (const char* e = getenv("MAGI_FORCE_G")) gmax = atoi(e);
     const bool force_global = getenv("MAGI_FORCE_GLOBAL_SCRATCH") != nullptr;
-    // rings [D][2 stages][4 blocks] + exchange [G*D tasks][2 stages][12 slots][32 lanes] + mbarriers
-    auto fixed_bytes = [&](int g) { return ((size_t)D * 2 * 4 * NCH * 32 + (size_t)g * D * 2 * 12 * 32 + 2 * D + 4 * g * D) * sizeof(double); };
+    // rings [D][kRingStages][4 blocks] + queues [G*D tasks][kXStages][kXSlots][32 lanes] + mbarriers (banded_kernel.cuh);
+    // the per-chain reduction area aliases the queues
+    constexpr int R = 3, S = 3, XS = 8;
+    auto fixed_bytes = [&](int g) { return ((size_t)D * R * 4 * NCH * 32 + (size_t)g * D * S * XS * 32 + 2 * R * D + 4 * S * g * D) * sizeof(double); };
     // As many chain-groups per block as fit 16 warps (2 warps per task); for long time axes the Ke scratch of that many
     // groups does not fit shared memory and goes to global memory (L2-resident): on LV n=1281 G=4 with L2 scratch ran in
     // 0.27 ms against 0.45 ms for G=1 with shared-memory scratch.
@@ -108,14 +118,14 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int& G, in
         if (2 * g * D > 16) continue;
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0 && force_global) continue;
-            size_t red = (size_t)g * 8 * D * RED * sizeof(double);
+            size_t red = 0;   // aliased
             size_t scr = pass == 0 ? banded_scratch_doubles_per_cta(g, D, NT) * sizeof(double) : 0;
             size_t tot = scr + fixed_bytes(g) + red;
             if (tot <= (size_t)smem_limit) { G = g; scratch_in_smem = (pass == 0); smem_bytes = tot; return; }
         }
     }
     G = 1; scratch_in_smem = 0;
-    smem_bytes = fixed_bytes(1) + (size_t)8 * D * RED * sizeof(double);
+    smem_bytes = fixed_bytes(1);
 }
 
 // one translation unit per model instantiates the kernels (banded_inst_*.cu), so they compile in parallel

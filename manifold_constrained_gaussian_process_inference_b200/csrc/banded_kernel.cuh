@@ -51,6 +51,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 // bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned done = 0;
+#pragma unroll 1
     for (unsigned it = 0; it < (1u << 26); ++it) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -58,18 +59,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
     __trap();
 }
+// waits for two barriers at once (the two try_wait round trips overlap)
+__device__ __forceinline__ void mbar_wait2(unsigned long long* bar_a, unsigned parity_a, unsigned long long* bar_b, unsigned parity_b) {
+    unsigned da = 0, db = 0;
+#pragma unroll 1
+    for (unsigned it = 0; it < (1u << 26); ++it) {
+        asm volatile("{\n.reg .pred p;\n.reg .pred r;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\nmbarrier.try_wait.parity.shared::cta.b64 r, [%4], %5;\n"
+                     "selp.u32 %0, 1, 0, p;\nselp.u32 %1, 1, 0, r;\n}\n"
+                     : "=r"(da), "=r"(db) : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b) : "memory");
+        if (da & db) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
 
-// One block = G chain-groups (8 chains each) x DW dimension slots, one warp per (group, dim) task, sweeping the time axis
-// TWO 8-time tiles per step (halves the per-step overhead -- window shifts, ring bookkeeping, barriers, address math -- and
-// gives the scheduler four independent DMMA accumulate chains plus two independent pointwise evaluations per step).
-//   A1: mx = m~ x_d, e = f - mx (sliding register windows), Ke = K~ e -> Ke scratch (shared memory); sum e.Ke
-//   A2: Cx = C~ x_d ; mt = m~^T Ke_d ; pointwise gradient incl. the ODE Jacobian terms (need Ke of all dimensions)
-// The four table-fragment blocks a step needs are staged ONCE per dimension in a double-buffered cp.async ring in shared
-// memory, shared by the G warps of that dimension (one named barrier per step), and read with 16-byte LDS (two chunks per
-// load): each fragment block leaves L2 once per block.
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -84,176 +89,158 @@ template <int D, class F> __device__ __forceinline__ void dispatch_dim(int d, F&
     if constexpr (D >= 5) { if (d == 4) { f(std::integral_constant<int, 4>{}); return; } }
 }
 
-// Warp-specialised K1.  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA warp
-// ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers.  The C warp owns the operand windows (x, e / Ke in
-// registers, sliding two 8-time tiles per step) and issues nothing but fragment LDS, window moves and DMMAs; the P warp does
-// every global load and all scalar FP64 work (ODE right-hand side, Jacobian terms, reductions, gradient stores) and hands
-// tiles back through a double-buffered exchange area in shared memory, with one mbarrier per direction and stage:
-//   A1  C(u): mx tiles (Ja, Ja+1) -> P        P(u): e = f(x, theta) - mx, x feed for step u+2 -> C(u+2)
-//       C(u): Ke tiles (Jb, Jb+1) = K~ e from the e window (lags two steps behind mx) -> Ke scratch; sum e.Ke
-//   A2  C(u): Cx, m^T Ke tiles (Jc, Jc+1) -> P    P(u): gradient incl. Jacobian terms, stores, reductions; x feed -> C(u+2)
-// The scalar FP64 work shares the FP64 unit with the DMMAs, but it no longer sits on the DMMA warps' in-order critical path
-// (measured before the split: a step's non-DMMA section took ~1500 cycles against 768 cycles of DMMA issue).
-// Fragment blocks arrive by TMA bulk copy into a double-buffered ring per dimension, shared by the G DMMA warps of that
-// dimension (named barrier per step), one 16-byte LDS per two chunks.
+// Warp-specialised K1 (v10).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
+// warp ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers.  The C warp owns the operand windows (x, e / Ke
+// in registers, sliding two 8-time tiles per step) and issues fragment LDS, window moves, DMMAs and its own (prefetched) x
+// loads; the P warp does all scalar FP64 work (ODE right-hand side, Jacobian terms, reductions, gradient stores).  All
+// hand-offs are ONE-DIRECTIONAL queues of kXStages stages in shared memory (a "full" and an "empty" mbarrier per stage), so
+// neither warp ever waits for a round trip through the other:
+//   A1  P(u): f(x, theta) at tiles (Ja, Ja+1) -> queue (P runs ahead)      C(u): mx = m~ x, e = f - mx straight into the e
+//       window (next step), Ke tiles (Jb, Jb+1) = K~ e -> Ke scratch, sum e.Ke
+//   A2  C(u): Cx, m~^T Ke tiles (Jc, Jc+1) -> queue (C runs ahead)         P(u): gradient incl. Jacobian terms, stores, sums
+// Fragment blocks arrive by TMA bulk copy into a kRingStages-deep ring per dimension, shared by the G DMMA warps of that
+// dimension: full[stage] (expect_tx) / empty[stage] (G arrivals) mbarriers, issued two steps ahead by one elected thread,
+// running straight through the A1 -> A2 boundary; one 16-byte LDS per two chunks.
+constexpr int kXStages = 3, kRingStages = 3, kXSlots = 8;
+
 template <int MODEL, int HB>
 __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs a) {
     using M = Ode<MODEL>;
     constexpr int D = M::D, K = M::K;
-    constexpr int NCH = 2 * HB + 2, LAGT = (HB + 1) / 2, WN = 2 * LAGT + 2 + HB, W2 = WN + 2;
+    constexpr int NCH = 2 * HB + 2, LAGT = (HB + 1) / 2, W2 = 2 * LAGT + 4 + HB;
     constexpr int RED = 4 + K;   // e.Ke, x.Cx, sse, bad flag, theta-gradient partials
-    constexpr int BLK = NCH * 32;               // doubles per fragment block (one view, one tile)
-    constexpr int XS = 12;                      // exchange slots per stage: A1 C->P 0..3 (mx), P->C 4..7 (e), 8..11 (x feed);
-                                                //                           A2 C->P 0..3 (Cx), 4..7 (m^T Ke), P->C 8..11 (x feed)
+    constexpr int BLKP = NCH * 64;              // doubles per fragment pair-block (one view, two tiles interleaved per lane)
+    constexpr int OFF = LAGT & 1, LAGP = LAGT >> 1;   // pair p of views m~, C~, m~^T holds tiles (2p - OFF, 2p - OFF + 1); of K~ (2p, 2p + 1)
+    constexpr int S = kXStages, R = kRingStages, XS = kXSlots;
     extern __shared__ __align__(128) double smem[];
     const int NT = a.NT, n = a.n, G = a.G;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
     const int ntask = G * D;
     const int role = warp / ntask;               // 0: DMMA warp (C), 1: pointwise warp (P)
-    const int task = warp % ntask, g = task % G, d_rt = task / G;
+    const int task = warp % ntask, g = task / D, d_rt = task % D;   // the two DMMA (pointwise) warps of an SM sub-partition share d when D = 2
     const size_t scr_doubles = (size_t)G * D * NT * 64;
-    // shared memory: [Ke scratch (if it fits)] [rings: D x 2 stages x 4 blocks] [exchange: tasks x 2 x XS x 32] [mbarriers] [red]
+    // shared memory: [Ke scratch (if it fits)] [rings: D x R stages x 2 pair-blocks] [queues: tasks x S x XS x 32] [mbarriers]
+    // (the per-chain reduction area `red` aliases the queues, which are dead by then)
     double* kscr = a.scratch_in_smem ? smem : a.scratch + (size_t)blockIdx.x * scr_doubles;
     double* rings = smem + (a.scratch_in_smem ? scr_doubles : 0);
-    double* ring = rings + (size_t)d_rt * 2 * 4 * BLK;
-    double* xch = rings + (size_t)D * 2 * 4 * BLK + (size_t)task * 2 * XS * 32 + lane;
-    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(rings + (size_t)D * 2 * 4 * BLK + (size_t)ntask * 2 * XS * 32);
-    unsigned long long* full = mbars + d_rt * 2;                 // ring stages of this dimension
-    unsigned long long* c2p = mbars + 2 * D + task * 4;          // [2] C -> P (tiles ready)
-    unsigned long long* p2c = c2p + 2;                           // [2] P -> C (results ready / stage consumed)
-    double* red = reinterpret_cast<double*>(mbars + 2 * D + 4 * ntask);   // [G*8][D][RED]
-    const int ring_threads = G * 32;
-    const bool ring_leader = (role == 0 && g == 0 && lane == 0);
+    double* ring = rings + (size_t)d_rt * R * 2 * BLKP;
+    double* xq_base = rings + (size_t)D * R * 2 * BLKP;
+    double* xq = xq_base + (size_t)task * S * XS * 32 + lane;
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(xq_base + (size_t)ntask * S * XS * 32);
+    unsigned long long* rfull = mbars + d_rt * 2 * R;            // ring stages of this dimension
+    unsigned long long* rempty = rfull + R;
+    unsigned long long* q1full = mbars + 2 * R * D + task * 4 * S;   // A1: P -> C (f tiles ready)
+    unsigned long long* q1empty = q1full + S;                        // A1: C -> P (stage consumed)
+    unsigned long long* q2full = q1empty + S;                        // A2: C -> P (Cx, m^T Ke tiles ready)
+    unsigned long long* q2empty = q2full + S;                        // A2: P -> C (stage consumed)
+    double* red = xq_base;                                           // [G*8][D][RED]
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * D + 4 * ntask; ++i) mbar_init(mbars + i, 1);
+        for (int dd = 0; dd < D; ++dd)
+            for (int i = 0; i < R; ++i) { mbar_init(mbars + dd * 2 * R + i, 1); mbar_init(mbars + dd * 2 * R + R + i, G); }
+        for (int i = 0; i < 4 * S * ntask; ++i) mbar_init(mbars + 2 * R * D + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    unsigned ring_use = 0;                       // ring stages consumed so far (parity tracking), C warps
-    unsigned xuse = 0;                           // exchange stages used so far, identical in the C and P warp of a task
 
     const long long chain = (long long)blockIdx.x * (G * 8) + g * 8 + gid;
     const bool cvalid = chain < a.n_chains;
     const double* xp = a.params + (cvalid ? chain : (long long)a.n_chains - 1) * a.pitch;
-    double th[M::KX];
-#pragma unroll
-    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
-    M::prepare(th);
     const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
-    long long wbar = 0, wp2c = 0, wfull = 0, wc2p = 0;     // MAGI_DBG_WAITS: cycles spent in each kind of wait (A2 only)
+    long long wq = 0, wfull = 0;                 // MAGI_DBG_WAITS: cycles spent waiting on the queues / the fragment ring
     if (a.dbg) tk0 = clock64();
 
-    auto stage_blocks = [&](unsigned use, const double* s0, const double* s1, const double* s2, const double* s3) {
-        if (ring_leader) {
-            double* dst = ring + (size_t)(use & 1) * 4 * BLK;
-            const unsigned nb = (s0 != nullptr) + (s1 != nullptr) + (s2 != nullptr) + (s3 != nullptr);
-            fence_proxy_async();
-            mbar_expect_tx(full + (use & 1), nb * BLK * 8);
-            if (s0) tma_bulk_g2s(dst, s0, BLK * 8, full + (use & 1));
-            if (s1) tma_bulk_g2s(dst + BLK, s1, BLK * 8, full + (use & 1));
-            if (s2) tma_bulk_g2s(dst + 2 * BLK, s2, BLK * 8, full + (use & 1));
-            if (s3) tma_bulk_g2s(dst + 3 * BLK, s3, BLK * 8, full + (use & 1));
-        }
-    };
     auto tile_ok = [&](int J) { return J >= 0 && J < NT; };
     auto ld2 = [&](const double* base, int J, double& v0, double& v1) {   // the two values this lane owns in tile J (0 outside)
         const int t0 = 8 * J + q, t1 = t0 + 4;
         v0 = (t0 >= 0 && t0 < n) ? base[t0] : 0.0;
         v1 = (t1 >= 0 && t1 < n) ? base[t1] : 0.0;
     };
-    const int uA1_end = (NT + 2 * LAGT + 4) / 2;     // last A1 step: Ke pair (2u - 4 - 2 LAGT, +1) reaches tile NT - 1
-    const int uA2_end = (NT - 1 + LAGT) / 2;
+    const int N1 = (NT + 2 * LAGT + 1) / 2 + 1;     // A1 steps: the Ke pair (2u - 2 - 2 LAGT, +1) reaches tile NT - 1
+    const int N2 = (NT - 1 + LAGT) / 2 + 1;         // A2 steps: the output pair (2u - LAGT, +1) reaches tile NT - 1
 
     // =========================== DMMA warp ===========================
-    auto c_warp = [&](auto dconst) {
-        constexpr int d = decltype(dconst)::value;
+    auto c_warp = [&]() {                          // one code path for every dimension (d only enters addresses)
+        const int d = d_rt;
         const double* xd = xp + (size_t)d * n;
+        const int NP = NT / 2 + 1;                   // pair-blocks per (view, dimension)
+        const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NP) * BLKP;   // m~
+        const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NP) * BLKP;   // C~
+        const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NP) * BLKP;   // K~
+        const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NP) * BLKP;   // m~^T
+        auto pair_ok = [&](int pp) { return pp >= 0 && pp < NP; };
+        // ring use r = A1 step r (r < N1) or A2 step r - N1; the elected thread streams the two pair-blocks of a use
+        // The producer duty rotates over the G DMMA warps of the dimension (use r is issued by warp g = r mod G), so that no warp
+        // is systematically slower than the others it shares the ring with.  No proxy fence: the stage was only READ through the
+        // generic proxy, and those reads are ordered before the consumers' mbarrier arrivals.
+        auto issue = [&](int r) {
+            if (r >= N1 + N2 || (r % G) != g) return;                    // warp-uniform
+            if (lane == 0) {
+                const int st = r % R;
+                if (r >= R) mbar_wait(rempty + st, ((r / R) - 1) & 1);   // every DMMA warp of this dimension released use r - R
+                const double *s0, *s1;
+                if (r < N1) {
+                    const int pa = r - LAGP, pb = r - 1 - LAGT;          // tiles (2r - LAGT, +1) of m~, (2r - 2 - 2 LAGT, +1) of K~
+                    s0 = pair_ok(pa) ? ft0 + (size_t)pa * BLKP : nullptr;  s1 = pair_ok(pb) ? ft2 + (size_t)pb * BLKP : nullptr;
+                } else {
+                    const int pc = r - N1 - LAGP;                        // tiles (2u - LAGT, +1) of C~ and m~^T
+                    s0 = pair_ok(pc) ? ft1 + (size_t)pc * BLKP : nullptr;  s1 = pair_ok(pc) ? ft3 + (size_t)pc * BLKP : nullptr;
+                }
+                double* dst = ring + (size_t)st * 2 * BLKP;
+                const unsigned nb = (s0 != nullptr) + (s1 != nullptr);
+                mbar_expect_tx(rfull + st, nb * BLKP * 8);
+                if (s0) tma_bulk_g2s(dst, s0, BLKP * 8, rfull + st);
+                if (s1) tma_bulk_g2s(dst + BLKP, s1, BLKP * 8, rfull + st);
+            }
+            __syncwarp();
+        };
+        issue(0); issue(1);
+        double acc_eke = 0.0;
+        // Every step is [header: ring producer + mbarrier waits (branches)] + [ONE basic block: fragment LDS, DMMAs, tile hand-off,
+        // scratch stores, window advance, prefetch of the next feed], so that the scheduler can fill the issue slots between DMMAs
+        // (one DMMA occupies the pipe for 16 clk) with everything else the warp has to do.
         // ---------------- A1 ----------------
         {
-            double xw[W2], ew[W2];
+            double xw[W2], ew[W2], nf[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < W2; ++i) { xw[i] = 0.0; ew[i] = 0.0; }
-            double acc_eke = 0.0;
             double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
-            const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NT) * BLK;
-            const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NT) * BLK;
-            auto stage_step = [&](int u, unsigned use) {
-                if (u <= uA1_end) {
-                    const int Ja = 2 * u - LAGT, Jb = 2 * u - 4 - 2 * LAGT;
-                    stage_blocks(use, tile_ok(Ja) ? ft0 + (size_t)Ja * BLK : nullptr, tile_ok(Ja + 1) ? ft0 + (size_t)(Ja + 1) * BLK : nullptr,
-                                 tile_ok(Jb) ? ft2 + (size_t)Jb * BLK : nullptr, tile_ok(Jb + 1) ? ft2 + (size_t)(Jb + 1) * BLK : nullptr);
-                }
-            };
-            named_barrier(1 + d, ring_threads);
-            stage_step(0, ring_use);
-            for (int u = 0; u <= uA1_end; ++u, ++ring_use, ++xuse) {
-#ifdef MAGI_DBG_WAITS1
+            ld2(xd, 0, xw[W2 - 4], xw[W2 - 3]); ld2(xd, 1, xw[W2 - 2], xw[W2 - 1]);   // window head of step 0: tiles 0, 1
+            auto a1_step = [&](int u, auto va_, auto vb_) {
+                constexpr bool VA = decltype(va_)::value, VB = decltype(vb_)::value;
+                const int st = u % R, qs = u % S;
+                double* xs = xq + (size_t)qs * XS * 32;
+#ifdef MAGI_DBG_WAITS
                 long long w0 = clock64();
 #endif
-                named_barrier(1 + d, ring_threads);          // all DMMA warps of this dimension finished step u-1
-#ifdef MAGI_DBG_WAITS1
-                long long w1 = clock64(); wbar += w1 - w0;
+                // fragments of this step; f tiles of this step from the pointwise warp (zero outside the time axis)
+                mbar_wait2(rfull + st, (u / R) & 1, q1full + qs, (u / S) & 1);
+#ifdef MAGI_DBG_WAITS
+                wfull += clock64() - w0;
 #endif
-                stage_step(u + 1, ring_use + 1);
-                double* xs = xch + (size_t)(xuse & 1) * XS * 32;
-                double fin[8];                               // e tiles of step u-2 (4) and x feed of this step (4)
-                if (xuse >= 2) mbar_wait(p2c + (xuse & 1), ((xuse - 2) >> 1) & 1);
-#ifdef MAGI_DBG_WAITS1
-                long long w2 = clock64(); wp2c += w2 - w1;
-#endif
-                if (u >= 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) fin[i] = xs[(4 + i) * 32];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) fin[i] = 0.0;
-                    ld2(xd, 2 * u, fin[4], fin[5]); ld2(xd, 2 * u + 1, fin[6], fin[7]);
-                }
-#pragma unroll
-                for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; ew[i] = ew[i + 4]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { ew[W2 - 4 + i] = fin[i]; xw[W2 - 4 + i] = fin[4 + i]; }
-#ifdef MAGI_DBG_WAITS1
-                long long w3 = clock64();
-#endif
-                mbar_wait(full + (ring_use & 1), (ring_use >> 1) & 1);
-#ifdef MAGI_DBG_WAITS1
-                wfull += clock64() - w3;
-#endif
-                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)(ring_use & 1) * 4 * BLK) + lane;
-                const int Ja = 2 * u - LAGT, Jb = 2 * u - 4 - 2 * LAGT;
-                const bool va = tile_ok(Ja) || tile_ok(Ja + 1), vb = tile_ok(Jb) || tile_ok(Jb + 1);
+                // x tiles (2u+2, 2u+3): loaded here, entered into the window at the end of the step (the DMMA block hides the
+                // latency; a loop-carried prefetch register would be touched by the loop's register moves first)
+                ld2(xd, 2 * u + 2, nf[0], nf[1]); ld2(xd, 2 * u + 3, nf[2], nf[3]);
+                const double f0 = xs[0], f1 = xs[32], f2 = xs[64], f3 = xs[96];
+                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)st * 2 * BLKP) + lane;
+                const int Jb = 2 * u - 2 - 2 * LAGT;
                 double m[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, k[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                if (va && vb) {
+                // one 16-byte LDS = chunk hh of BOTH tiles of the pair: the two DMMAs it feeds belong to different accumulate chains
 #pragma unroll
-                    for (int hp = 0; hp < NCH / 2; ++hp) {
-                        const double2 fa0 = fr[hp * 32], fa1 = fr[BLK / 2 + hp * 32], fb0 = fr[BLK + hp * 32], fb1 = fr[3 * BLK / 2 + hp * 32];
-                        dmma884(m[0][0], m[0][1], xw[2 * hp], fa0.x);         dmma884(m[1][0], m[1][1], xw[2 * hp + 2], fa1.x);
-                        dmma884(k[0][0], k[0][1], ew[2 * hp], fb0.x);         dmma884(k[1][0], k[1][1], ew[2 * hp + 2], fb1.x);
-                        dmma884(m[0][0], m[0][1], xw[2 * hp + 1], fa0.y);     dmma884(m[1][0], m[1][1], xw[2 * hp + 3], fa1.y);
-                        dmma884(k[0][0], k[0][1], ew[2 * hp + 1], fb0.y);     dmma884(k[1][0], k[1][1], ew[2 * hp + 3], fb1.y);
+                for (int hh = 0; hh < NCH; ++hh) {
+                    if constexpr (VA) {
+                        const double2 fa = fr[hh * 32];
+                        dmma884(m[0][0], m[0][1], xw[hh], fa.x);  dmma884(m[1][0], m[1][1], xw[hh + 2], fa.y);   // likelihoods.jl:129
                     }
-                } else if (va) {
-#pragma unroll
-                    for (int hp = 0; hp < NCH / 2; ++hp) {
-                        const double2 fa0 = fr[hp * 32], fa1 = fr[BLK / 2 + hp * 32];
-                        dmma884(m[0][0], m[0][1], xw[2 * hp], fa0.x);         dmma884(m[1][0], m[1][1], xw[2 * hp + 2], fa1.x);
-                        dmma884(m[0][0], m[0][1], xw[2 * hp + 1], fa0.y);     dmma884(m[1][0], m[1][1], xw[2 * hp + 3], fa1.y);
-                    }
-                } else if (vb) {
-#pragma unroll
-                    for (int hp = 0; hp < NCH / 2; ++hp) {
-                        const double2 fb0 = fr[BLK + hp * 32], fb1 = fr[3 * BLK / 2 + hp * 32];
-                        dmma884(k[0][0], k[0][1], ew[2 * hp], fb0.x);         dmma884(k[1][0], k[1][1], ew[2 * hp + 2], fb1.x);
-                        dmma884(k[0][0], k[0][1], ew[2 * hp + 1], fb0.y);     dmma884(k[1][0], k[1][1], ew[2 * hp + 3], fb1.y);
+                    if constexpr (VB) {
+                        const double2 fb = fr[BLKP / 2 + hh * 32];
+                        dmma884(k[0][0], k[0][1], ew[hh], fb.x);  dmma884(k[1][0], k[1][1], ew[hh + 2], fb.y);   // likelihoods.jl:132
                     }
                 }
-                // hand mx to the pointwise warp (likelihoods.jl:129)
-                xs[0] = m[0][0]; xs[32] = m[0][1]; xs[64] = m[1][0]; xs[96] = m[1][1];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c2p + (xuse & 1));
-                if (vb) {
+                if (lane == 0) { mbar_arrive(q1empty + qs); mbar_arrive(rempty + st); }
+                issue(u + 2);                                    // by now the other warps have normally released use u - 1
+                if constexpr (VB) {
 #pragma unroll
                     for (int tt = 0; tt < 2; ++tt) {
                         if (tile_ok(Jb + tt)) {
@@ -264,141 +251,148 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                         }
                     }
                 }
-            }
+                // advance the windows to step u+1: x tiles (2u+2, 2u+3); e = f - mx of this step (likelihoods.jl:130)
+#pragma unroll
+                for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; ew[i] = ew[i + 4]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xw[W2 - 4 + i] = nf[i];
+                ew[W2 - 4] = f0 - m[0][0]; ew[W2 - 3] = f1 - m[0][1]; ew[W2 - 2] = f2 - m[1][0]; ew[W2 - 1] = f3 - m[1][1];
+            };
+            // m~ pairs are valid for u in [LAGP, NP + LAGP), K~ pairs for u in [LAGT + 1, NP + LAGT + 1): one loop per variant
+            // (a single loop over a four-way branch makes every path end in its own register assignment, i.e. ~80 moves per step)
+            const int ua0 = min(LAGP, N1), ua1 = min(NP + LAGP, N1), ub0 = min(LAGT + 1, N1);
+            int u = 0;
+#pragma unroll 1
+            for (; u < ua0; ++u) a1_step(u, std::false_type{}, std::false_type{});
+#pragma unroll 1
+            for (; u < ub0; ++u) a1_step(u, std::true_type{}, std::false_type{});
+#pragma unroll 1
+            for (; u < ua1; ++u) a1_step(u, std::true_type{}, std::true_type{});
+#pragma unroll 1
+            for (; u < N1; ++u) a1_step(u, std::false_type{}, std::true_type{});
             acc_eke = quad_sum(acc_eke);
-            if (q == 0) red[((size_t)(g * 8 + gid) * D + d) * RED + 0] = acc_eke;
         }
         if (a.dbg) tk1 = clock64();
         __syncthreads();                                     // Ke of every dimension is in the scratch
         if (a.dbg) tk2 = clock64();
         // ---------------- A2 ----------------
         {
-            double xw[W2], kw[W2];
+            double xw[W2], kw[W2], nf[4], nk[4];
 #pragma unroll
             for (int i = 0; i < W2; ++i) { xw[i] = 0.0; kw[i] = 0.0; }
             const double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
-            const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NT) * BLK;
-            const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NT) * BLK;
-            auto stage_step = [&](int u, unsigned use) {
-                if (u <= uA2_end) {
-                    const int Jc = 2 * u - LAGT;
-                    stage_blocks(use, tile_ok(Jc) ? ft1 + (size_t)Jc * BLK : nullptr, tile_ok(Jc + 1) ? ft1 + (size_t)(Jc + 1) * BLK : nullptr,
-                                 tile_ok(Jc) ? ft3 + (size_t)Jc * BLK : nullptr, tile_ok(Jc + 1) ? ft3 + (size_t)(Jc + 1) * BLK : nullptr);
-                }
-            };
-            named_barrier(1 + d, ring_threads);
-            stage_step(0, ring_use);
-            for (int u = 0; u <= uA2_end; ++u, ++ring_use, ++xuse) {
-#ifdef MAGI_DBG_WAITS
-                long long w0 = clock64();
-#endif
-                named_barrier(1 + d, ring_threads);
-#ifdef MAGI_DBG_WAITS
-                long long w1 = clock64(); wbar += w1 - w0;
-#endif
-                stage_step(u + 1, ring_use + 1);
-                double* xs = xch + (size_t)(xuse & 1) * XS * 32;
-                double feed[4];
-                if (xuse >= 2) mbar_wait(p2c + (xuse & 1), ((xuse - 2) >> 1) & 1);     // P consumed this stage two steps ago
-#ifdef MAGI_DBG_WAITS
-                long long w2 = clock64(); wp2c += w2 - w1;
-#endif
-                if (u >= 2) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) feed[i] = xs[(8 + i) * 32];
-                } else { ld2(xd, 2 * u, feed[0], feed[1]); ld2(xd, 2 * u + 1, feed[2], feed[3]); }
-#pragma unroll
-                for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; kw[i] = kw[i + 4]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xw[W2 - 4 + i] = feed[i];
+            auto load_feed = [&](int u, double (&fx)[4], double (&fk)[4]) {
+                ld2(xd, 2 * u, fx[0], fx[1]); ld2(xd, 2 * u + 1, fx[2], fx[3]);
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt) {
                     const bool ok = tile_ok(2 * u + tt);
-                    kw[W2 - 4 + 2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64] : 0.0;
-                    kw[W2 - 3 + 2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64 + 32] : 0.0;
+                    fk[2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64] : 0.0;
+                    fk[2 * tt + 1] = ok ? ks[(size_t)(2 * u + tt) * 64 + 32] : 0.0;
                 }
-#ifdef MAGI_DBG_WAITS
-                long long w3 = clock64();
-#endif
-                mbar_wait(full + (ring_use & 1), (ring_use >> 1) & 1);
-#ifdef MAGI_DBG_WAITS
-                wfull += clock64() - w3;
-#endif
-                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)(ring_use & 1) * 4 * BLK) + lane;
-                const int Jc = 2 * u - LAGT;
-                double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                if (tile_ok(Jc) || tile_ok(Jc + 1)) {
+            };
+            load_feed(0, nf, nk);
 #pragma unroll
-                    for (int hp = 0; hp < NCH / 2; ++hp) {
-                        const double2 fa0 = fr[hp * 32], fa1 = fr[BLK / 2 + hp * 32], fb0 = fr[BLK + hp * 32], fb1 = fr[3 * BLK / 2 + hp * 32];
-                        dmma884(c[0][0], c[0][1], xw[2 * hp], fa0.x);          dmma884(c[1][0], c[1][1], xw[2 * hp + 2], fa1.x);      // likelihoods.jl:133
-                        dmma884(um[0][0], um[0][1], kw[2 * hp], fb0.x);        dmma884(um[1][0], um[1][1], kw[2 * hp + 2], fb1.x);    // likelihoods.jl:192
-                        dmma884(c[0][0], c[0][1], xw[2 * hp + 1], fa0.y);      dmma884(c[1][0], c[1][1], xw[2 * hp + 3], fa1.y);
-                        dmma884(um[0][0], um[0][1], kw[2 * hp + 1], fb0.y);    dmma884(um[1][0], um[1][1], kw[2 * hp + 3], fb1.y);
+            for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
+            auto a2_step = [&](int u, auto v_) {
+                constexpr bool V = decltype(v_)::value;
+                const int r = N1 + u;
+                const int st = r % R, qs = u % S;
+                double* xs = xq + (size_t)qs * XS * 32;
+#ifdef MAGI_DBG_WAITS
+                long long w0 = clock64();
+#endif
+                // fragments of this step; the pointwise warp has read the tiles of step u - S
+                if (u >= S) mbar_wait2(rfull + st, (r / R) & 1, q2empty + qs, ((u / S) - 1) & 1);
+                else mbar_wait(rfull + st, (r / R) & 1);
+#ifdef MAGI_DBG_WAITS
+                wfull += clock64() - w0;
+#endif
+                load_feed(u + 1, nf, nk);                        // x and Ke tiles (2u+2, 2u+3), entered at the end of the step
+                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)st * 2 * BLKP) + lane;
+                double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                if constexpr (V) {
+#pragma unroll
+                    for (int hh = 0; hh < NCH; ++hh) {
+                        const double2 fa = fr[hh * 32], fb = fr[BLKP / 2 + hh * 32];
+                        dmma884(c[0][0], c[0][1], xw[hh], fa.x);    dmma884(c[1][0], c[1][1], xw[hh + 2], fa.y);     // likelihoods.jl:133
+                        dmma884(um[0][0], um[0][1], kw[hh], fb.x);  dmma884(um[1][0], um[1][1], kw[hh + 2], fb.y);   // likelihoods.jl:192
                     }
                 }
                 xs[0] = c[0][0]; xs[32] = c[0][1]; xs[64] = c[1][0]; xs[96] = c[1][1];
                 xs[128] = um[0][0]; xs[160] = um[0][1]; xs[192] = um[1][0]; xs[224] = um[1][1];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(c2p + (xuse & 1));
-            }
+                if (lane == 0) { mbar_arrive(q2full + qs); mbar_arrive(rempty + st); }
+                issue(r + 2);
+#pragma unroll
+                for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; kw[i] = kw[i + 4]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
+            };
+            const int uc0 = min(LAGP, N2), uc1 = min(NP + LAGP, N2);
+            int u = 0;
+#pragma unroll 1
+            for (; u < uc0; ++u) a2_step(u, std::false_type{});
+#pragma unroll 1
+            for (; u < uc1; ++u) a2_step(u, std::true_type{});
+#pragma unroll 1
+            for (; u < N2; ++u) a2_step(u, std::false_type{});
         }
         if (a.dbg) tk3 = clock64();
+        __syncthreads();                                     // the queues are dead: `red` may overwrite them
+        if (q == 0) red[((size_t)(g * 8 + gid) * D + d) * RED + 0] = acc_eke;
     };
 
     // =========================== pointwise warp ===========================
     auto p_warp = [&](auto dconst) {
         constexpr int d = decltype(dconst)::value;
-        const double* xd = xp + (size_t)d * n;
-        // ---------------- A1: e = f(x, theta) - mx ----------------
-        // (global loads of step u+1 are issued before step u is processed: the load latency is off the exchange's critical path)
+        double th[M::KX];
+#pragma unroll
+        for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+        M::prepare(th);
+        // ---------------- A1: f(x, theta), ahead of the DMMA warp ----------------
+        // (global loads of step u+1 are issued before step u is processed)
         {
-            double xa[2][2][D], feed[4], nxa[2][2][D], nfeed[4];
-            auto load_a1 = [&](int u, double (&X)[2][2][D], double (&F)[4]) {
+            double xa[2][2][D], nxa[2][2][D];
+            auto load_a1 = [&](int u, double (&X)[2][2][D]) {
                 const int Ja = 2 * u - LAGT;
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) ld2(xp + (size_t)dd * n, tile_ok(Ja + tt) ? Ja + tt : -4, X[tt][0][dd], X[tt][1][dd]);
-                ld2(xd, 2 * u + 4, F[0], F[1]); ld2(xd, 2 * u + 5, F[2], F[3]);      // window feed of step u+2
             };
-            load_a1(0, nxa, nfeed);
-            for (int u = 0; u <= uA1_end; ++u, ++xuse) {
-                const int Ja = 2 * u - LAGT;
+            load_a1(0, nxa);
+            for (int u = 0; u < N1; ++u) {
+                const int Ja = 2 * u - LAGT, qs = u % S;
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
                     for (int pt = 0; pt < 2; ++pt)
 #pragma unroll
                         for (int dd = 0; dd < D; ++dd) xa[tt][pt][dd] = nxa[tt][pt][dd];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) feed[i] = nfeed[i];
-                if (u < uA1_end) load_a1(u + 1, nxa, nfeed);
-                double* xs = xch + (size_t)(xuse & 1) * XS * 32;
-#ifdef MAGI_DBG_WAITS1
-                long long w0 = clock64();
-#endif
-                mbar_wait(c2p + (xuse & 1), (xuse >> 1) & 1);
-#ifdef MAGI_DBG_WAITS1
-                wc2p += clock64() - w0;
-#endif
-                const double mm[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}};
+                if (u + 1 < N1) load_a1(u + 1, nxa);
+                double fv[2][2];
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
                     for (int pt = 0; pt < 2; ++pt) {
                         const int t = 8 * (Ja + tt) + q + 4 * pt;
-                        const double ev = M::f(d, xa[tt][pt], th) - mm[tt][pt];           // likelihoods.jl:130
-                        xs[(4 + 2 * tt + pt) * 32] = (tile_ok(Ja + tt) && t < n) ? ev : 0.0;
+                        const double v = M::f(d, xa[tt][pt], th);
+                        fv[tt][pt] = (tile_ok(Ja + tt) && t < n) ? v : 0.0;
                     }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xs[(8 + i) * 32] = feed[i];
+                double* xs = xq + (size_t)qs * XS * 32;
+#ifdef MAGI_DBG_WAITS
+                long long w0 = clock64();
+#endif
+                if (u >= S) mbar_wait(q1empty + qs, ((u / S) - 1) & 1);
+#ifdef MAGI_DBG_WAITS
+                wq += clock64() - w0;
+#endif
+                xs[0] = fv[0][0]; xs[32] = fv[0][1]; xs[64] = fv[1][0]; xs[96] = fv[1][1];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p2c + (xuse & 1));
+                if (lane == 0) mbar_arrive(q1full + qs);
             }
         }
-        __syncthreads();
-        // ---------------- A2: pointwise gradient ----------------
+        // A2 prologue that does not depend on the Ke scratch
         double acc_xcx = 0.0, acc_sse = 0.0;
         double gth[K];
 #pragma unroll
@@ -414,8 +408,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         const double obs_scale = (1.0 / (sigma_d * sigma_d)) * inv_b3;
         const double* yd = a.yobs + (size_t)d * n;
         double* gout = (a.grad != nullptr && cvalid) ? a.grad + chain * a.pitch + (size_t)d * n : nullptr;
-        double nxa[2][2][D], nyv[2][2], nfeed[4];
-        auto load_a2 = [&](int u, double (&X)[2][2][D], double (&Y)[2][2], double (&F)[4]) {
+        double nxa[2][2][D], nyv[2][2];
+        auto load_a2 = [&](int u, double (&X)[2][2][D], double (&Y)[2][2]) {
             const int Jc = 2 * u - LAGT;
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
@@ -424,12 +418,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 for (int dd = 0; dd < D; ++dd) ld2(xp + (size_t)dd * n, J, X[tt][0][dd], X[tt][1][dd]);
                 ld2(yd, J, Y[tt][0], Y[tt][1]);
             }
-            ld2(xd, 2 * u + 4, F[0], F[1]); ld2(xd, 2 * u + 5, F[2], F[3]);
         };
-        load_a2(0, nxa, nyv, nfeed);
-        for (int u = 0; u <= uA2_end; ++u, ++xuse) {
-            const int Jc = 2 * u - LAGT;
-            double xa[2][2][D], wv[2][2][D], yv[2][2], feed[4];
+        load_a2(0, nxa, nyv);
+        __syncthreads();
+        // ---------------- A2: pointwise gradient ----------------
+        for (int u = 0; u < N2; ++u) {
+            const int Jc = 2 * u - LAGT, qs = u % S;
+            double xa[2][2][D], wv[2][2][D], yv[2][2];
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
@@ -438,9 +433,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     for (int dd = 0; dd < D; ++dd) xa[tt][pt][dd] = nxa[tt][pt][dd];
                     yv[tt][pt] = nyv[tt][pt];
                 }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) feed[i] = nfeed[i];
-            if (u < uA2_end) load_a2(u + 1, nxa, nyv, nfeed);
+            if (u + 1 < N2) load_a2(u + 1, nxa, nyv);
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 const int J = tile_ok(Jc + tt) ? Jc + tt : -4;
@@ -451,15 +444,17 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     wv[tt][1][dd] = (J < 0) ? 0.0 : wsrc[32] * inv_b1;
                 }
             }
-            double* xs = xch + (size_t)(xuse & 1) * XS * 32;
+            double* xs = xq + (size_t)qs * XS * 32;
 #ifdef MAGI_DBG_WAITS
             long long w0 = clock64();
 #endif
-            mbar_wait(c2p + (xuse & 1), (xuse >> 1) & 1);
+            mbar_wait(q2full + qs, (u / S) & 1);
 #ifdef MAGI_DBG_WAITS
-            wc2p += clock64() - w0;
+            wq += clock64() - w0;
 #endif
             const double cxv[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}}, mtv[2][2] = {{xs[128], xs[160]}, {xs[192], xs[224]}};
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q2empty + qs);            // the stage is free again while the gradient is computed
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
 #pragma unroll
@@ -484,16 +479,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     if (valid && gout != nullptr) gout[t] = gv;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xs[(8 + i) * 32] = feed[i];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p2c + (xuse & 1));
         }
         acc_xcx = quad_sum(acc_xcx);
         acc_sse = quad_sum(acc_sse);
 #pragma unroll
         for (int i = 0; i < K; ++i) gth[i] = quad_sum(gth[i]);
         const unsigned badm = __ballot_sync(0xffffffffu, bad);
+        __syncthreads();                                     // the queues are dead: `red` may overwrite them
         if (q == 0) {
             double* r = red + ((size_t)(g * 8 + gid) * D + d) * RED;
             r[1] = acc_xcx;
@@ -504,13 +496,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         }
     };
 
-    if (role == 0) dispatch_dim<D>(d_rt, c_warp);
+    if (role == 0) c_warp();
     else dispatch_dim<D>(d_rt, p_warp);
     __syncthreads();
     if (a.dbg && lane == 0) {
         long long* o = a.dbg + ((size_t)blockIdx.x * ntask + task) * 8;
-        if (role == 0) { o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tk3 - tk2; o[3] = clock64() - tk3; o[4] = wbar; o[5] = wp2c; o[6] = wfull; }
-        else o[7] = wc2p;
+        if (role == 0) { o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tk3 - tk2; o[3] = clock64() - tk3; o[4] = wfull; o[5] = wq; }
+        else o[7] = wq;
     }
 
     // ---------------- final: one thread per chain ----------------

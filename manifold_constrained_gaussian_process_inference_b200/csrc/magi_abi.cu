@@ -126,7 +126,7 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
 
     h->dense_mode = (h->geom.HB > kMaxHB) || h->model == MAGI_MODEL_L96;
     if (!h->dense_mode) {
-        size_t fsz = (size_t)4 * h->D * h->geom.NT * h->geom.NCH * 32;
+        size_t fsz = fragtab_doubles(h->n, h->b, h->D);
         if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
         banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
     }
@@ -204,8 +204,9 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
         cudaMemcpy(v.data(), d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < nblk * nwarp; ++i) { for (int j = 0; j < 8; ++j) s[j] += (double)v[i * 8 + j]; }
-        fprintf(stderr, "[magi dbg] blocks=%d warps=%d G=%d H=%d smem=%zu  avg cycles: A1=%.0f sync=%.0f A2=%.0f sync=%.0f (A2 waits: C ring barrier=%.0f, C for P=%.0f, C for TMA=%.0f, P for C=%.0f)\n", nblk, nwarp, h->G, h->H, h->smem_bytes,
-                s[0] / (nblk * nwarp), s[1] / (nblk * nwarp), s[2] / (nblk * nwarp), s[3] / (nblk * nwarp), s[4] / (nblk * nwarp), s[5] / (nblk * nwarp), s[6] / (nblk * nwarp), s[7] / (nblk * nwarp));
+        const double nw = (double)nblk * nwarp;
+        fprintf(stderr, "[magi dbg] blocks=%d tasks=%d G=%d smem=%zu  avg cycles per DMMA warp: A1=%.0f sync=%.0f A2=%.0f tail=%.0f (with -DMAGI_DBG_WAITS: DMMA warp waits ring=%.0f queue=%.0f, pointwise warp waits queue=%.0f)\n",
+                nblk, nwarp, h->G, h->smem_bytes, s[0] / nw, s[1] / nw, s[2] / nw, s[3] / nw, s[4] / nw, s[5] / nw, s[7] / nw);
         cudaFree(d_dbg);
     }
     return MAGI_OK;

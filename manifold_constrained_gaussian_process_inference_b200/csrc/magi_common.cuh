@@ -42,7 +42,7 @@ struct BandedArgs {
     const double* params;
     double* ll;
     double* grad;               // may be null (value only)
-    const double* fragtab;      // [4 views][D][NT][NCH][32]
+    const double* fragtab;      // [4 views][D][NT/2+1 pairs][NCH][32 lanes][2 tiles]
     const double* yobs;         // [D][n], non-finite = missing
     const int* nobs;            // [D]
     const double* sigma_init;   // [D]
@@ -55,6 +55,7 @@ struct BandedArgs {
 // launches (defined in the .cu files)
 cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
                                  int n, int b, int D, cudaStream_t st);
+size_t fragtab_doubles(int n, int b, int D);
 size_t banded_scratch_doubles_per_cta(int G, int D, int NT);
 void banded_pick_config(int model_D, int model_K, int NT, int HB, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes);
 bool model_dims(int model, int& D, int& K);
