@@ -134,10 +134,17 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     unsigned long long* q2full = q1empty + S;                        // A2: C -> P (Cx, m^T Ke tiles ready)
     unsigned long long* q2empty = q2full + S;                        // A2: P -> C (stage consumed)
     double* red = xq_base;                                           // [G*8][D][RED]
-    if (threadIdx.x == 0) {
-        for (int dd = 0; dd < D; ++dd)
-            for (int i = 0; i < R; ++i) { mbar_init(mbars + dd * 2 * R + i, 1); mbar_init(mbars + dd * 2 * R + R + i, G); }
-        for (int i = 0; i < 4 * S * ntask; ++i) mbar_init(mbars + 2 * R * D + i, 1);
+#ifdef MAGI_POISON_SMEM
+    {   // debug: every shared-memory word starts as NaN, so that a read of a never-written location shows up deterministically
+        const size_t tot = (a.scratch_in_smem ? scr_doubles : 0) + (size_t)D * R * 2 * BLKP + (size_t)ntask * S * XS * 32;
+        for (size_t i = threadIdx.x; i < tot; i += blockDim.x) smem[i] = __longlong_as_double(0x7ff8000000000000LL | (long long)(MAGI_POISON_SMEM));
+        __syncthreads();
+    }
+#endif
+    {   // mbarrier init, one barrier per thread: [D][rfull R | rempty R] then [task][4 S]
+        const int nring = 2 * R * D, nall = nring + 4 * S * ntask;
+        for (int i = threadIdx.x; i < nall; i += blockDim.x)
+            mbar_init(mbars + i, (i < nring && (i % (2 * R)) >= R) ? G : 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -260,16 +267,29 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             };
             // m~ pairs are valid for u in [LAGP, NP + LAGP), K~ pairs for u in [LAGT + 1, NP + LAGT + 1): one loop per variant
             // (a single loop over a four-way branch makes every path end in its own register assignment, i.e. ~80 moves per step)
-            const int ua0 = min(LAGP, N1), ua1 = min(NP + LAGP, N1), ub0 = min(LAGT + 1, N1);
-            int u = 0;
+            int bp[6] = {0, LAGP, LAGT + 1, NP + LAGP, NP + LAGT + 1, N1};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) bp[i] = min(bp[i], N1);
+            if (bp[2] > bp[3]) { const int t = bp[2]; bp[2] = bp[3]; bp[3] = t; }       // very short time axes: the m~ range ends before the K~ range starts
 #pragma unroll 1
-            for (; u < ua0; ++u) a1_step(u, std::false_type{}, std::false_type{});
+            for (int seg = 0; seg < 5; ++seg) {
+                const int u0 = bp[seg], u1 = bp[seg + 1];
+                if (u0 >= u1) continue;
+                const bool va = pair_ok(u0 - LAGP), vb = pair_ok(u0 - 1 - LAGT);
+                if (va && vb) {
 #pragma unroll 1
-            for (; u < ub0; ++u) a1_step(u, std::true_type{}, std::false_type{});
+                    for (int u = u0; u < u1; ++u) a1_step(u, std::true_type{}, std::true_type{});
+                } else if (va) {
 #pragma unroll 1
-            for (; u < ua1; ++u) a1_step(u, std::true_type{}, std::true_type{});
+                    for (int u = u0; u < u1; ++u) a1_step(u, std::true_type{}, std::false_type{});
+                } else if (vb) {
 #pragma unroll 1
-            for (; u < N1; ++u) a1_step(u, std::false_type{}, std::true_type{});
+                    for (int u = u0; u < u1; ++u) a1_step(u, std::false_type{}, std::true_type{});
+                } else {
+#pragma unroll 1
+                    for (int u = u0; u < u1; ++u) a1_step(u, std::false_type{}, std::false_type{});
+                }
+            }
             acc_eke = quad_sum(acc_eke);
         }
         if (a.dbg) tk1 = clock64();
