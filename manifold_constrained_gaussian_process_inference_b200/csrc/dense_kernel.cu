@@ -262,6 +262,11 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         DCK(cudaMalloc(&h->d_dense_work, sizeof(double) * need), "cudaMalloc dense work space");
         h->dense_work_cap = need;
     }
+    if (!h->d_sk_work) {
+        DCK(cudaMalloc(&h->d_sk_work, sizeof(double) * kStreamKWorkDoubles), "cudaMalloc stream-K work space");
+        DCK(cudaMalloc(&h->d_sk_flags, sizeof(unsigned) * kStreamKSlots), "cudaMalloc stream-K flags");
+        DCK(cudaMemsetAsync(h->d_sk_flags, 0, sizeof(unsigned) * kStreamKSlots, st), "memset stream-K flags");
+    }
     double* MXE = h->d_dense_work;            // MX, then E in place
     double* KE = MXE + plane * D;
     double* CX = KE + plane * D;
@@ -275,6 +280,8 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         g.B = B; g.rsB = rsB; g.csB = csB; g.bsB1 = bsB; g.bsB2 = 0;
         g.C = C; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = 0;
         g.M = n; g.N = n_chains; g.K = n; g.nb1 = 1 << 30; g.alpha = 1.0; g.beta = 0.0;
+        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch;
+        if (g.sk_epoch == 0) g.sk_epoch = ++h->sk_epoch;
         cudaError_t e = launch_gemm(g, D, st);
         h->launches++;
         return e;

@@ -37,7 +37,7 @@ extern "C" int magi_destroy(magi_handle* h) {
     for (int i = 0; i < 7; ++i) free_dev(h->d_dense[i]);
     free_dev(h->d_fragtab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
-    free_dev(h->d_dense_work); free_dev(h->d_dense_ops);
+    free_dev(h->d_dense_work); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
     hmc_free(h);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 3; ++i) if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);

@@ -29,6 +29,9 @@ struct magi_handle {
     double* d_dense_ops = nullptr;     // band-truncated dense Cinv~, mphi~, Kinv~ ([3][D][n x n]) for the dense path
     double* d_dense_work = nullptr;
     size_t dense_work_cap = 0;
+    double* d_sk_work = nullptr;       // stream-K partial tiles and flags (gemm_f64.cuh)
+    unsigned* d_sk_flags = nullptr;
+    unsigned sk_epoch = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};   // H2D / kernel / D2H overlap in the host-buffer batched call
     long long launches = 0;
