@@ -247,6 +247,7 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
         if (rc) return rc;
         CK(cudaStreamSynchronize(h->stream), "stream sync");
         int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
+        { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
         const int per = ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32;
         int i = 0;
         for (int c0 = 0; c0 < n_chains; c0 += per, ++i) {
