@@ -100,17 +100,17 @@ size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)G *
 // Chooses chain-groups per block (G), time segments (H), concurrently processed dimensions (DW) and where the Ke scratch
 // lives.  Preference: 16 warps per block (one block per SM, <= 128 registers), as many chain-groups as possible sharing a
 // fragment ring, two time segments when the time axis is long enough to amortise the halo.
-void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
+void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
     const int RED = 4 + K, NCH = 2 * HB + 2;
     DW = D;
     H = 1;
-    int gmax = 4;
+    if (gmax < 1 || gmax > 4) gmax = 4;
     if (const char* e = getenv("MAGI_FORCE_G")) gmax = atoi(e);
     const bool force_global = getenv("MAGI_FORCE_GLOBAL_SCRATCH") != nullptr;
     // rings [D][kRingStages][4 blocks] + queues [G*D tasks][kXStages][kXSlots][32 lanes] + mbarriers (banded_kernel.cuh);
     // the per-chain reduction area aliases the queues
     constexpr int R = 3, S = 3, XS = 8;
-    auto fixed_bytes = [&](int g) { return ((size_t)D * R * 4 * NCH * 32 + (size_t)g * D * S * XS * 32 + 2 * R * D + 4 * S * g * D) * sizeof(double); };
+    auto fixed_bytes = [&](int g) { return ((size_t)D * R * 4 * NCH * 32 + (size_t)g * D * S * XS * 32 + 4 * R * D + 4 * S * g * D) * sizeof(double); };
     // As many chain-groups per block as fit 16 warps (2 warps per task); for long time axes the Ke scratch of that many
     // groups does not fit shared memory and goes to global memory (L2-resident): on LV n=1281 G=4 with L2 scratch ran in
     // 0.27 ms against 0.45 ms for G=1 with shared-memory scratch.

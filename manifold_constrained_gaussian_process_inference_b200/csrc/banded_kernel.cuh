@@ -52,7 +52,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned done = 0;
 #pragma unroll 1
-    for (unsigned it = 0; it < (1u << 26); ++it) {
+    for (unsigned it = 0; it < (1u << 22); ++it) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) return;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __device__ __forceinline__ void mbar_wait2(unsigned long long* bar_a, unsigned parity_a, unsigned long long* bar_b, unsigned parity_b) {
     unsigned da = 0, db = 0;
 #pragma unroll 1
-    for (unsigned it = 0; it < (1u << 26); ++it) {
+    for (unsigned it = 0; it < (1u << 22); ++it) {
         asm volatile("{\n.reg .pred p;\n.reg .pred r;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\nmbarrier.try_wait.parity.shared::cta.b64 r, [%4], %5;\n"
                      "selp.u32 %0, 1, 0, p;\nselp.u32 %1, 1, 0, r;\n}\n"
                      : "=r"(da), "=r"(db) : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b) : "memory");
@@ -123,13 +123,16 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     // (the per-chain reduction area `red` aliases the queues, which are dead by then)
     double* kscr = a.scratch_in_smem ? smem : a.scratch + (size_t)blockIdx.x * scr_doubles;
     double* rings = smem + (a.scratch_in_smem ? scr_doubles : 0);
-    double* ring = rings + (size_t)d_rt * R * 2 * BLKP;
+    double* ringA = rings + (size_t)d_rt * R * 2 * BLKP;          // A1: m~ pair-blocks (pointwise warps); A2: C~ pair-blocks
+    double* ringB = ringA + (size_t)R * BLKP;                      // A1: K~ pair-blocks; A2: m~^T pair-blocks (DMMA warps)
     double* xq_base = rings + (size_t)D * R * 2 * BLKP;
     double* xq = xq_base + (size_t)task * S * XS * 32 + lane;
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(xq_base + (size_t)ntask * S * XS * 32);
-    unsigned long long* rfull = mbars + d_rt * 2 * R;            // ring stages of this dimension
-    unsigned long long* rempty = rfull + R;
-    unsigned long long* q1full = mbars + 2 * R * D + task * 4 * S;   // A1: P -> C (f tiles ready)
+    unsigned long long* afull = mbars + d_rt * 4 * R;            // ring A stages of this dimension
+    unsigned long long* aempty = afull + R;
+    unsigned long long* bfull = aempty + R;                      // ring B
+    unsigned long long* bempty = bfull + R;
+    unsigned long long* q1full = mbars + 4 * R * D + task * 4 * S;   // A1: P -> C (e tiles ready)
     unsigned long long* q1empty = q1full + S;                        // A1: C -> P (stage consumed)
     unsigned long long* q2full = q1empty + S;                        // A2: C -> P (Cx, m^T Ke tiles ready)
     unsigned long long* q2empty = q2full + S;                        // A2: P -> C (stage consumed)
@@ -142,9 +145,9 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     }
 #endif
     {   // mbarrier init, one barrier per thread: [D][rfull R | rempty R] then [task][4 S]
-        const int nring = 2 * R * D, nall = nring + 4 * S * ntask;
+        const int nring = 4 * R * D, nall = nring + 4 * S * ntask;
         for (int i = threadIdx.x; i < nall; i += blockDim.x)
-            mbar_init(mbars + i, (i < nring && (i % (2 * R)) >= R) ? G : 1);
+            mbar_init(mbars + i, (i < nring && ((i / R) & 1)) ? G : 1);     // the "empty" barriers take one arrival per consumer warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -163,133 +166,109 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         v0 = (t0 >= 0 && t0 < n) ? base[t0] : 0.0;
         v1 = (t1 >= 0 && t1 < n) ? base[t1] : 0.0;
     };
-    const int N1 = (NT + 2 * LAGT + 1) / 2 + 1;     // A1 steps: the Ke pair (2u - 2 - 2 LAGT, +1) reaches tile NT - 1
+    const int NP = NT / 2 + 1;                      // pair-blocks per (view, dimension)
+    constexpr int LE = LAGP + OFF;                  // the K~ pair pb is computed right after e pair pb + LE has entered the window
     const int N2 = (NT - 1 + LAGT) / 2 + 1;         // A2 steps: the output pair (2u - LAGT, +1) reaches tile NT - 1
+    auto pair_ok = [&](int pp) { return pp >= 0 && pp < NP; };
+    // One elected thread streams pair-block `src` (null: nothing to load, the barrier still completes) into stage r mod R of
+    // a ring, after every consumer warp has released use r - R.  The producer duty rotates over the G consumer warps of the
+    // dimension (use r is issued by warp g = r mod G), so that no warp is systematically slower than the ones it shares the
+    // ring with.  No proxy fence: the stage was only READ through the generic proxy, before the consumers' arrivals.
+    auto ring_issue = [&](int r, double* buf, unsigned long long* full, unsigned long long* empty, const double* src, double* buf2, const double* src2) {
+        if ((r % G) != g) return;                                         // warp-uniform
+        if (lane == 0) {
+            const int st = r % R;
+            if (r >= R) mbar_wait(empty + st, ((r / R) - 1) & 1);
+            const unsigned nb = (src != nullptr) + (src2 != nullptr);
+            mbar_expect_tx(full + st, nb * BLKP * 8);
+            if (src) tma_bulk_g2s(buf + (size_t)st * BLKP, src, BLKP * 8, full + st);
+            if (src2) tma_bulk_g2s(buf2 + (size_t)st * BLKP, src2, BLKP * 8, full + st);
+        }
+        __syncwarp();
+    };
 
     // =========================== DMMA warp ===========================
     auto c_warp = [&]() {                          // one code path for every dimension (d only enters addresses)
         const int d = d_rt;
         const double* xd = xp + (size_t)d * n;
-        const int NP = NT / 2 + 1;                   // pair-blocks per (view, dimension)
-        const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NP) * BLKP;   // m~
         const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NP) * BLKP;   // C~
         const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NP) * BLKP;   // K~
         const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NP) * BLKP;   // m~^T
-        auto pair_ok = [&](int pp) { return pp >= 0 && pp < NP; };
-        // ring use r = A1 step r (r < N1) or A2 step r - N1; the elected thread streams the two pair-blocks of a use
-        // The producer duty rotates over the G DMMA warps of the dimension (use r is issued by warp g = r mod G), so that no warp
-        // is systematically slower than the others it shares the ring with.  No proxy fence: the stage was only READ through the
-        // generic proxy, and those reads are ordered before the consumers' mbarrier arrivals.
-        auto issue = [&](int r) {
-            if (r >= N1 + N2 || (r % G) != g) return;                    // warp-uniform
-            if (lane == 0) {
-                const int st = r % R;
-                if (r >= R) mbar_wait(rempty + st, ((r / R) - 1) & 1);   // every DMMA warp of this dimension released use r - R
-                const double *s0, *s1;
-                if (r < N1) {
-                    const int pa = r - LAGP, pb = r - 1 - LAGT;          // tiles (2r - LAGT, +1) of m~, (2r - 2 - 2 LAGT, +1) of K~
-                    s0 = pair_ok(pa) ? ft0 + (size_t)pa * BLKP : nullptr;  s1 = pair_ok(pb) ? ft2 + (size_t)pb * BLKP : nullptr;
-                } else {
-                    const int pc = r - N1 - LAGP;                        // tiles (2u - LAGT, +1) of C~ and m~^T
-                    s0 = pair_ok(pc) ? ft1 + (size_t)pc * BLKP : nullptr;  s1 = pair_ok(pc) ? ft3 + (size_t)pc * BLKP : nullptr;
-                }
-                double* dst = ring + (size_t)st * 2 * BLKP;
-                const unsigned nb = (s0 != nullptr) + (s1 != nullptr);
-                mbar_expect_tx(rfull + st, nb * BLKP * 8);
-                if (s0) tma_bulk_g2s(dst, s0, BLKP * 8, rfull + st);
-                if (s1) tma_bulk_g2s(dst + BLKP, s1, BLKP * 8, rfull + st);
+        // ring B use r: A1 K~ pair r (r < NP); A2 step u = r - NP: C~ pair into ring A's buffer and m~^T pair into ring B's,
+        // both signalled on ring B's barriers (the pointwise warps no longer use ring A then)
+        auto issue_b = [&](int r) {
+            if (r < NP) ring_issue(r, ringB, bfull, bempty, ft2 + (size_t)r * BLKP, nullptr, nullptr);
+            else if (r < NP + N2) {
+                const int pc = r - NP - LAGP;
+                ring_issue(r, ringB, bfull, bempty, pair_ok(pc) ? ft3 + (size_t)pc * BLKP : nullptr, ringA, pair_ok(pc) ? ft1 + (size_t)pc * BLKP : nullptr);
             }
-            __syncwarp();
         };
-        issue(0); issue(1);
+        issue_b(0);
+        if (NP > 1) issue_b(1);
         double acc_eke = 0.0;
-        // Every step is [header: ring producer + mbarrier waits (branches)] + [ONE basic block: fragment LDS, DMMAs, tile hand-off,
-        // scratch stores, window advance, prefetch of the next feed], so that the scheduler can fill the issue slots between DMMAs
-        // (one DMMA occupies the pipe for 16 clk) with everything else the warp has to do.
-        // ---------------- A1 ----------------
+        // ---------------- A1: Ke = K~ e (likelihoods.jl:132); e tiles come from the pointwise warp ----------------
         {
-            double xw[W2], ew[W2], nf[4] = {0.0, 0.0, 0.0, 0.0};
+            double ew[W2];
 #pragma unroll
-            for (int i = 0; i < W2; ++i) { xw[i] = 0.0; ew[i] = 0.0; }
+            for (int i = 0; i < W2; ++i) ew[i] = 0.0;
             double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
-            ld2(xd, 0, xw[W2 - 4], xw[W2 - 3]); ld2(xd, 1, xw[W2 - 2], xw[W2 - 1]);   // window head of step 0: tiles 0, 1
-            auto a1_step = [&](int u, auto va_, auto vb_) {
-                constexpr bool VA = decltype(va_)::value, VB = decltype(vb_)::value;
-                const int st = u % R, qs = u % S;
-                double* xs = xq + (size_t)qs * XS * 32;
+            auto a1_step = [&](int i, auto in_, auto vb_) {
+                constexpr bool IN = decltype(in_)::value, VB = decltype(vb_)::value;   // IN: an e pair arrives; VB: a K~ pair is computed
+                const int pb = i - LE, st = pb % R, qs = i % S;
+                double e4[4] = {0.0, 0.0, 0.0, 0.0};
 #ifdef MAGI_DBG_WAITS
                 long long w0 = clock64();
 #endif
-                // fragments of this step; f tiles of this step from the pointwise warp (zero outside the time axis)
-                mbar_wait2(rfull + st, (u / R) & 1, q1full + qs, (u / S) & 1);
+                if constexpr (IN && VB) mbar_wait2(q1full + qs, (i / S) & 1, bfull + st, (pb / R) & 1);
+                else if constexpr (IN) mbar_wait(q1full + qs, (i / S) & 1);
+                else if constexpr (VB) mbar_wait(bfull + st, (pb / R) & 1);
 #ifdef MAGI_DBG_WAITS
                 wfull += clock64() - w0;
 #endif
-                // x tiles (2u+2, 2u+3): loaded here, entered into the window at the end of the step (the DMMA block hides the
-                // latency; a loop-carried prefetch register would be touched by the loop's register moves first)
-                ld2(xd, 2 * u + 2, nf[0], nf[1]); ld2(xd, 2 * u + 3, nf[2], nf[3]);
-                const double f0 = xs[0], f1 = xs[32], f2 = xs[64], f3 = xs[96];
-                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)st * 2 * BLKP) + lane;
-                const int Jb = 2 * u - 2 - 2 * LAGT;
-                double m[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, k[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                // one 16-byte LDS = chunk hh of BOTH tiles of the pair: the two DMMAs it feeds belong to different accumulate chains
-#pragma unroll
-                for (int hh = 0; hh < NCH; ++hh) {
-                    if constexpr (VA) {
-                        const double2 fa = fr[hh * 32];
-                        dmma884(m[0][0], m[0][1], xw[hh], fa.x);  dmma884(m[1][0], m[1][1], xw[hh + 2], fa.y);   // likelihoods.jl:129
-                    }
-                    if constexpr (VB) {
-                        const double2 fb = fr[BLKP / 2 + hh * 32];
-                        dmma884(k[0][0], k[0][1], ew[hh], fb.x);  dmma884(k[1][0], k[1][1], ew[hh + 2], fb.y);   // likelihoods.jl:132
-                    }
+                if constexpr (IN) {
+                    const double* xs = xq + (size_t)qs * XS * 32;
+                    e4[0] = xs[0]; e4[1] = xs[32]; e4[2] = xs[64]; e4[3] = xs[96];
                 }
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(q1empty + qs); mbar_arrive(rempty + st); }
-                issue(u + 2);                                    // by now the other warps have normally released use u - 1
+#pragma unroll
+                for (int j = 0; j < W2 - 4; ++j) ew[j] = ew[j + 4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ew[W2 - 4 + j] = e4[j];
                 if constexpr (VB) {
+                    const double2* fr = reinterpret_cast<const double2*>(ringB + (size_t)st * BLKP) + lane;
+                    double k[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    // one 16-byte LDS = chunk hh of BOTH tiles of the pair: the two DMMAs it feeds belong to different accumulate chains
+#pragma unroll
+                    for (int hh = 0; hh < NCH; ++hh) {
+                        const double2 fb = fr[hh * 32];
+                        dmma884(k[0][0], k[0][1], ew[hh], fb.x);  dmma884(k[1][0], k[1][1], ew[hh + 2], fb.y);
+                    }
+                    __syncwarp();
+                    if (lane == 0) { if (IN) mbar_arrive(q1empty + qs); mbar_arrive(bempty + st); }
+                    if (pb + 2 < NP) issue_b(pb + 2);          // (the A2 uses wait for the block barrier: the pointwise warps may still read ring A)
 #pragma unroll
                     for (int tt = 0; tt < 2; ++tt) {
-                        if (tile_ok(Jb + tt)) {
-                            ks[(size_t)(Jb + tt) * 64] = k[tt][0];             // likelihoods.jl:132
-                            ks[(size_t)(Jb + tt) * 64 + 32] = k[tt][1];
+                        if (tile_ok(2 * pb + tt)) {
+                            ks[(size_t)(2 * pb + tt) * 64] = k[tt][0];
+                            ks[(size_t)(2 * pb + tt) * 64 + 32] = k[tt][1];
                             acc_eke += ew[HB + 2 * tt] * k[tt][0];             // likelihoods.jl:146
                             acc_eke += ew[HB + 2 * tt + 1] * k[tt][1];
                         }
                     }
+                } else if constexpr (IN) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(q1empty + qs);
                 }
-                // advance the windows to step u+1: x tiles (2u+2, 2u+3); e = f - mx of this step (likelihoods.jl:130)
-#pragma unroll
-                for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; ew[i] = ew[i + 4]; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xw[W2 - 4 + i] = nf[i];
-                ew[W2 - 4] = f0 - m[0][0]; ew[W2 - 3] = f1 - m[0][1]; ew[W2 - 2] = f2 - m[1][0]; ew[W2 - 1] = f3 - m[1][1];
             };
-            // m~ pairs are valid for u in [LAGP, NP + LAGP), K~ pairs for u in [LAGT + 1, NP + LAGT + 1): one loop per variant
-            // (a single loop over a four-way branch makes every path end in its own register assignment, i.e. ~80 moves per step)
-            int bp[6] = {0, LAGP, LAGT + 1, NP + LAGP, NP + LAGT + 1, N1};
-#pragma unroll
-            for (int i = 0; i < 6; ++i) bp[i] = min(bp[i], N1);
-            if (bp[2] > bp[3]) { const int t = bp[2]; bp[2] = bp[3]; bp[3] = t; }       // very short time axes: the m~ range ends before the K~ range starts
+            // e pairs arrive for i in [0, NP), K~ pairs are computed for i in [LE, NP + LE): one loop per combination
+            int i = 0;
 #pragma unroll 1
-            for (int seg = 0; seg < 5; ++seg) {
-                const int u0 = bp[seg], u1 = bp[seg + 1];
-                if (u0 >= u1) continue;
-                const bool va = pair_ok(u0 - LAGP), vb = pair_ok(u0 - 1 - LAGT);
-                if (va && vb) {
+            for (; i < min(LE, NP); ++i) a1_step(i, std::true_type{}, std::false_type{});
 #pragma unroll 1
-                    for (int u = u0; u < u1; ++u) a1_step(u, std::true_type{}, std::true_type{});
-                } else if (va) {
+            for (; i < LE; ++i) a1_step(i, std::false_type{}, std::false_type{});       // (only when NP < LE)
 #pragma unroll 1
-                    for (int u = u0; u < u1; ++u) a1_step(u, std::true_type{}, std::false_type{});
-                } else if (vb) {
+            for (; i < NP; ++i) a1_step(i, std::true_type{}, std::true_type{});
 #pragma unroll 1
-                    for (int u = u0; u < u1; ++u) a1_step(u, std::false_type{}, std::true_type{});
-                } else {
-#pragma unroll 1
-                    for (int u = u0; u < u1; ++u) a1_step(u, std::false_type{}, std::false_type{});
-                }
-            }
+            for (; i < NP + LE; ++i) a1_step(i, std::false_type{}, std::true_type{});
             acc_eke = quad_sum(acc_eke);
         }
         if (a.dbg) tk1 = clock64();
@@ -315,25 +294,26 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
             auto a2_step = [&](int u, auto v_) {
                 constexpr bool V = decltype(v_)::value;
-                const int r = N1 + u;
+                const int r = NP + u;
                 const int st = r % R, qs = u % S;
                 double* xs = xq + (size_t)qs * XS * 32;
 #ifdef MAGI_DBG_WAITS
                 long long w0 = clock64();
 #endif
                 // fragments of this step; the pointwise warp has read the tiles of step u - S
-                if (u >= S) mbar_wait2(rfull + st, (r / R) & 1, q2empty + qs, ((u / S) - 1) & 1);
-                else mbar_wait(rfull + st, (r / R) & 1);
+                if (u >= S) mbar_wait2(bfull + st, (r / R) & 1, q2empty + qs, ((u / S) - 1) & 1);
+                else mbar_wait(bfull + st, (r / R) & 1);
 #ifdef MAGI_DBG_WAITS
                 wfull += clock64() - w0;
 #endif
                 load_feed(u + 1, nf, nk);                        // x and Ke tiles (2u+2, 2u+3), entered at the end of the step
-                const double2* fr = reinterpret_cast<const double2*>(ring + (size_t)st * 2 * BLKP) + lane;
+                const double2* fra = reinterpret_cast<const double2*>(ringA + (size_t)st * BLKP) + lane;
+                const double2* frb = reinterpret_cast<const double2*>(ringB + (size_t)st * BLKP) + lane;
                 double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
                 if constexpr (V) {
 #pragma unroll
                     for (int hh = 0; hh < NCH; ++hh) {
-                        const double2 fa = fr[hh * 32], fb = fr[BLKP / 2 + hh * 32];
+                        const double2 fa = fra[hh * 32], fb = frb[hh * 32];
                         dmma884(c[0][0], c[0][1], xw[hh], fa.x);    dmma884(c[1][0], c[1][1], xw[hh + 2], fa.y);     // likelihoods.jl:133
                         dmma884(um[0][0], um[0][1], kw[hh], fb.x);  dmma884(um[1][0], um[1][1], kw[hh + 2], fb.y);   // likelihoods.jl:192
                     }
@@ -341,13 +321,14 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 xs[0] = c[0][0]; xs[32] = c[0][1]; xs[64] = c[1][0]; xs[96] = c[1][1];
                 xs[128] = um[0][0]; xs[160] = um[0][1]; xs[192] = um[1][0]; xs[224] = um[1][1];
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(q2full + qs); mbar_arrive(rempty + st); }
-                issue(r + 2);
+                if (lane == 0) { mbar_arrive(q2full + qs); mbar_arrive(bempty + st); }
+                issue_b(r + 2);
 #pragma unroll
                 for (int i = 0; i < W2 - 4; ++i) { xw[i] = xw[i + 4]; kw[i] = kw[i + 4]; }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
             };
+            issue_b(NP); issue_b(NP + 1);                        // (after the block barrier: ring A's buffer is free now)
             const int uc0 = min(LAGP, N2), uc1 = min(NP + LAGP, N2);
             int u = 0;
 #pragma unroll 1
@@ -369,48 +350,71 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
         for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
         M::prepare(th);
-        // ---------------- A1: f(x, theta), ahead of the DMMA warp ----------------
-        // (global loads of step u+1 are issued before step u is processed)
+        // ---------------- A1: mx = m~ x_d (likelihoods.jl:129), e = f(x, theta) - mx (:130) -> queue, ahead of the DMMA warp ----------------
+        // step u: output tiles (Ja, Ja+1) = (2u - LAGT, +1) = m~ pair pa = u - LAGP; the x window head is at tiles (2u, 2u+1)
         {
-            double xa[2][2][D], nxa[2][2][D];
-            auto load_a1 = [&](int u, double (&X)[2][2][D]) {
-                const int Ja = 2 * u - LAGT;
+            const double* xd = xp + (size_t)d * n;
+            const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NP) * BLKP;   // m~
+            auto issue_a = [&](int r) { if (r < NP) ring_issue(r, ringA, afull, aempty, ft0 + (size_t)r * BLKP, nullptr, nullptr); };
+            issue_a(0); issue_a(1);
+            double xw[W2], nf[4];
+#pragma unroll
+            for (int i = 0; i < W2; ++i) xw[i] = 0.0;
+            ld2(xd, 0, xw[W2 - 4], xw[W2 - 3]); ld2(xd, 1, xw[W2 - 2], xw[W2 - 1]);   // window head of step 0: tiles 0, 1
+            auto a1_step = [&](int u, auto va_) {
+                constexpr bool VA = decltype(va_)::value;
+                const int Ja = 2 * u - LAGT, pa = u - LAGP, st = pa % R, qs = pa % S;
+                if constexpr (VA) {
+#ifdef MAGI_DBG_WAITS
+                    long long w0 = clock64();
+#endif
+                    if (pa >= S) mbar_wait2(afull + st, (pa / R) & 1, q1empty + qs, ((pa / S) - 1) & 1);   // fragments; queue stage free
+                    else mbar_wait(afull + st, (pa / R) & 1);
+#ifdef MAGI_DBG_WAITS
+                    wq += clock64() - w0;
+#endif
+                }
+                ld2(xd, 2 * u + 2, nf[0], nf[1]); ld2(xd, 2 * u + 3, nf[2], nf[3]);    // window feed of step u+1 (entered at the end)
+                double xo[2][2][D];                  // the other components at the output points (this one is in the window)
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                    for (int dd = 0; dd < D; ++dd) ld2(xp + (size_t)dd * n, tile_ok(Ja + tt) ? Ja + tt : -4, X[tt][0][dd], X[tt][1][dd]);
-            };
-            load_a1(0, nxa);
-            for (int u = 0; u < N1; ++u) {
-                const int Ja = 2 * u - LAGT, qs = u % S;
+                    for (int dd = 0; dd < D; ++dd)
+                        if (dd != d) ld2(xp + (size_t)dd * n, (VA && tile_ok(Ja + tt)) ? Ja + tt : -4, xo[tt][0][dd], xo[tt][1][dd]);
+                if constexpr (VA) {
+                    const double2* fr = reinterpret_cast<const double2*>(ringA + (size_t)st * BLKP) + lane;
+                    double m[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-                for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-                    for (int pt = 0; pt < 2; ++pt)
-#pragma unroll
-                        for (int dd = 0; dd < D; ++dd) xa[tt][pt][dd] = nxa[tt][pt][dd];
-                if (u + 1 < N1) load_a1(u + 1, nxa);
-                double fv[2][2];
-#pragma unroll
-                for (int tt = 0; tt < 2; ++tt)
-#pragma unroll
-                    for (int pt = 0; pt < 2; ++pt) {
-                        const int t = 8 * (Ja + tt) + q + 4 * pt;
-                        const double v = M::f(d, xa[tt][pt], th);
-                        fv[tt][pt] = (tile_ok(Ja + tt) && t < n) ? v : 0.0;
+                    for (int hh = 0; hh < NCH; ++hh) {
+                        const double2 fa = fr[hh * 32];
+                        dmma884(m[0][0], m[0][1], xw[hh], fa.x);  dmma884(m[1][0], m[1][1], xw[hh + 2], fa.y);
                     }
-                double* xs = xq + (size_t)qs * XS * 32;
-#ifdef MAGI_DBG_WAITS
-                long long w0 = clock64();
-#endif
-                if (u >= S) mbar_wait(q1empty + qs, ((u / S) - 1) & 1);
-#ifdef MAGI_DBG_WAITS
-                wq += clock64() - w0;
-#endif
-                xs[0] = fv[0][0]; xs[32] = fv[0][1]; xs[64] = fv[1][0]; xs[96] = fv[1][1];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(q1full + qs);
-            }
+                    double ev[2][2];
+#pragma unroll
+                    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                        for (int pt = 0; pt < 2; ++pt) {
+                            const int t = 8 * (Ja + tt) + q + 4 * pt;
+                            xo[tt][pt][d] = xw[HB + 2 * tt + pt];
+                            const double v = M::f(d, xo[tt][pt], th) - m[tt][pt];
+                            ev[tt][pt] = (tile_ok(Ja + tt) && t < n) ? v : 0.0;
+                        }
+                    double* xs = xq + (size_t)qs * XS * 32;
+                    xs[0] = ev[0][0]; xs[32] = ev[0][1]; xs[64] = ev[1][0]; xs[96] = ev[1][1];
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(q1full + qs); mbar_arrive(aempty + st); }
+                    issue_a(pa + 2);
+                }
+#pragma unroll
+                for (int j = 0; j < W2 - 4; ++j) xw[j] = xw[j + 4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xw[W2 - 4 + j] = nf[j];
+            };
+            int u = 0;
+#pragma unroll 1
+            for (; u < LAGP; ++u) a1_step(u, std::false_type{});
+#pragma unroll 1
+            for (; u < NP + LAGP; ++u) a1_step(u, std::true_type{});
         }
         // A2 prologue that does not depend on the Ke scratch
         double acc_xcx = 0.0, acc_sse = 0.0;

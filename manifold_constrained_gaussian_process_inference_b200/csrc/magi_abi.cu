@@ -128,7 +128,7 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
     if (!h->dense_mode) {
         size_t fsz = fragtab_doubles(h->n, h->b, h->D);
         if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
-        banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
+        banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, 4, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
     }
     if (h->setup_mode != MAGI_SETUP_INJECT) {
         rc = run_device_setup(h);
@@ -154,6 +154,17 @@ int ensure_capacity(magi_handle* h, int n_chains) {
     CK(cudaMalloc(&h->d_ll, sizeof(double) * cap), "cudaMalloc ll staging");
     h->cap_chains = cap;
     return MAGI_OK;
+}
+
+// Block shape per call: four chain-groups per block share one fragment ring (best per-SM throughput), but a batch of at most
+// 16 chains per SM would leave half the machine idle -- two groups per block then (tools/g_sweep.py: LV n=1281, 2048 chains
+// 0.249 -> 0.191 ms; FN n=201, 2048 chains 0.057 -> 0.047 ms).
+static void select_block_shape(magi_handle* h, int n_chains) {
+    const int gmax = (n_chains <= 16 * h->sm_count) ? 2 : 4;
+    if (gmax != h->gmax_cur) {
+        banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, gmax, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
+        h->gmax_cur = gmax;
+    }
 }
 
 static int ensure_scratch(magi_handle* h, int n_chains) {
@@ -182,6 +193,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     if (h->dense_mode) return eval_dense_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
     int rc = refresh_fragtab(h, st);
     if (rc) return rc;
+    select_block_shape(h, n_chains);
     rc = ensure_scratch(h, n_chains);
     if (rc) return rc;
     BandedArgs a;
@@ -240,15 +252,16 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     // instead of H2D + kernel + D2H in sequence).  The banded kernel keeps its scratch in shared memory, so chunks are
     // independent; other configurations take the single-stream path.
     const int chunk_min = 1024;
+    int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
+    { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
+    const int per = nchunks > 0 ? ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32 : n_chains;
+    if (!h->dense_mode && h->tables_ready) select_block_shape(h, per);      // the shape every chunk will run with
     if (n_chains >= 2 * chunk_min && !h->dense_mode && h->scratch_in_smem && h->tables_ready) {
         for (int i = 0; i < 3; ++i)
             if (!h->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
         rc = refresh_fragtab(h, h->stream);
         if (rc) return rc;
         CK(cudaStreamSynchronize(h->stream), "stream sync");
-        int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
-        { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
-        const int per = ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32;
         int i = 0;
         for (int c0 = 0; c0 < n_chains; c0 += per, ++i) {
             const int nc = (n_chains - c0 < per) ? n_chains - c0 : per;

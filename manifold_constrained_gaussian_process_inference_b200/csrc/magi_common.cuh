@@ -57,7 +57,7 @@ cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mph
                                  int n, int b, int D, cudaStream_t st);
 size_t fragtab_doubles(int n, int b, int D);
 size_t banded_scratch_doubles_per_cta(int G, int D, int NT);
-void banded_pick_config(int model_D, int model_K, int NT, int HB, int smem_limit, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes);
+void banded_pick_config(int model_D, int model_K, int NT, int HB, int smem_limit, int gmax, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes);
 bool model_dims(int model, int& D, int& K);
 
 }  // namespace magi

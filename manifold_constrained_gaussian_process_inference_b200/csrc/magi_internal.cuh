@@ -36,7 +36,7 @@ struct magi_handle {
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};   // H2D / kernel / D2H overlap in the host-buffer batched call
     long long launches = 0;
     int smem_limit = 0, sm_count = 148;
-    int G = 2, H = 1, DW = 1, scratch_in_smem = 1;
+    int G = 2, H = 1, DW = 1, scratch_in_smem = 1, gmax_cur = 4;
     size_t smem_bytes = 0;
     std::vector<int> repaired_c, repaired_k;
     void* hmc = nullptr;     // on-device sampler state (hmc.cu)
