@@ -433,6 +433,20 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         const double* yd = a.yobs + (size_t)d * n;
         double* gout = (a.grad != nullptr && cvalid) ? a.grad + chain * a.pitch + (size_t)d * n : nullptr;
         double nxa[2][2][D], nyv[2][2];
+        // INTERIOR steps (both output tiles inside the time axis, all 16 times < n) run without bounds predicates and selects
+        auto load_a2_int = [&](int u, double (&X)[2][2][D], double (&Y)[2][2]) {
+            const int Jc = 2 * u - LAGT;
+            const double* px = xp + 8 * Jc + q;
+            const double* py = yd + 8 * Jc + q;
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                for (int pt = 0; pt < 2; ++pt) {
+#pragma unroll
+                    for (int dd = 0; dd < D; ++dd) X[tt][pt][dd] = px[(size_t)dd * n + 8 * tt + 4 * pt];
+                    Y[tt][pt] = py[8 * tt + 4 * pt];
+                }
+        };
         auto load_a2 = [&](int u, double (&X)[2][2][D], double (&Y)[2][2]) {
             const int Jc = 2 * u - LAGT;
 #pragma unroll
@@ -443,10 +457,12 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 ld2(yd, J, Y[tt][0], Y[tt][1]);
             }
         };
+        auto interior = [&](int u) { const int Jc = 2 * u - LAGT; return u < N2 && Jc >= 0 && 8 * (Jc + 1) + 7 < n; };
         load_a2(0, nxa, nyv);
         __syncthreads();
         // ---------------- A2: pointwise gradient ----------------
-        for (int u = 0; u < N2; ++u) {
+        auto a2_step = [&](int u, auto int_) {
+            constexpr bool INTERIOR = decltype(int_)::value;     // this step AND the next one are interior
             const int Jc = 2 * u - LAGT, qs = u % S;
             double xa[2][2][D], wv[2][2][D], yv[2][2];
 #pragma unroll
@@ -457,15 +473,27 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     for (int dd = 0; dd < D; ++dd) xa[tt][pt][dd] = nxa[tt][pt][dd];
                     yv[tt][pt] = nyv[tt][pt];
                 }
-            if (u + 1 < N2) load_a2(u + 1, nxa, nyv);
+            if constexpr (INTERIOR) load_a2_int(u + 1, nxa, nyv);
+            else if (u + 1 < N2) load_a2(u + 1, nxa, nyv);
+            if constexpr (INTERIOR) {
+                const double* wsrc = kscr + ((size_t)(g * D) * NT + Jc) * 64 + lane;
 #pragma unroll
-            for (int tt = 0; tt < 2; ++tt) {
-                const int J = tile_ok(Jc + tt) ? Jc + tt : -4;
+                for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
-                for (int dd = 0; dd < D; ++dd) {
-                    const double* wsrc = kscr + ((size_t)(g * D + dd) * NT + (J < 0 ? 0 : J)) * 64 + lane;
-                    wv[tt][0][dd] = (J < 0) ? 0.0 : wsrc[0] * inv_b1;  // likelihoods.jl:201
-                    wv[tt][1][dd] = (J < 0) ? 0.0 : wsrc[32] * inv_b1;
+                    for (int dd = 0; dd < D; ++dd) {
+                        wv[tt][0][dd] = wsrc[((size_t)dd * NT + tt) * 64] * inv_b1;         // likelihoods.jl:201
+                        wv[tt][1][dd] = wsrc[((size_t)dd * NT + tt) * 64 + 32] * inv_b1;
+                    }
+            } else {
+#pragma unroll
+                for (int tt = 0; tt < 2; ++tt) {
+                    const int J = tile_ok(Jc + tt) ? Jc + tt : -4;
+#pragma unroll
+                    for (int dd = 0; dd < D; ++dd) {
+                        const double* wsrc = kscr + ((size_t)(g * D + dd) * NT + (J < 0 ? 0 : J)) * 64 + lane;
+                        wv[tt][0][dd] = (J < 0) ? 0.0 : wsrc[0] * inv_b1;  // likelihoods.jl:201
+                        wv[tt][1][dd] = (J < 0) ? 0.0 : wsrc[32] * inv_b1;
+                    }
                 }
             }
             double* xs = xq + (size_t)qs * XS * 32;
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                 for (int pt = 0; pt < 2; ++pt) {
                     const int t = 8 * (Jc + tt) + q + 4 * pt;
-                    const bool valid = tile_ok(Jc + tt) && t < n;
+                    const bool valid = INTERIOR || (tile_ok(Jc + tt) && t < n);
                     const double cx = cxv[tt][pt], mt = mtv[tt][pt];
                     const double* xv = xa[tt][pt];
                     const double* w = wv[tt][pt];
@@ -503,6 +531,15 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     if (valid && gout != nullptr) gout[t] = gv;
                 }
             }
+        };
+        {
+            int u = 0;
+#pragma unroll 1
+            for (; u < N2 && !(interior(u) && interior(u + 1)); ++u) a2_step(u, std::false_type{});
+#pragma unroll 1
+            for (; u < N2 && interior(u) && interior(u + 1); ++u) a2_step(u, std::true_type{});
+#pragma unroll 1
+            for (; u < N2; ++u) a2_step(u, std::false_type{});
         }
         acc_xcx = quad_sum(acc_xcx);
         acc_sse = quad_sum(acc_sse);
