@@ -89,6 +89,31 @@ def test_batched_parity_random(pkg, model, n, b, nc, kw):
     assert l1 == ll[nc // 2] and np.array_equal(g1, g[nc // 2])
 
 
+@pytest.mark.parametrize("model,n,b,nc,what", [
+    ("lv", 264, 263, 9600, "stream-K GEMM, 2 tile rows + 8 remainder rows (skinny kernel), 75 tile columns"),
+    ("fn", 300, 299, 3300, "stream-K GEMM with predicated edge tiles in both directions"),
+    ("fn", 201, 20, 2368, "K1 with two chain-groups per block, last batch size before the switch"),
+    ("fn", 201, 20, 2369, "K1 with four chain-groups per block, partial last block"),
+    ("fn", 201, 20, 5000, "K1 pipelined host call: chunks of different block shapes"),
+])
+def test_large_batch_paths(pkg, model, n, b, nc, what):
+    """Code paths that only large batches reach (persistent stream-K GEMM of the dense mode; the per-call block shape of the
+    banded kernel; the chunked host call): a sample of chains against the oracle, every chain against a small-batch call."""
+    base = H.make_problem(model=model, n=n, b=b, n_chains=8, seed=n + nc, T=0.06 * n)
+    rng = np.random.default_rng(nc)
+    params = np.repeat(base["params"], (nc + 7) // 8, axis=0)[:nc] + 1e-3 * rng.normal(size=(nc, base["params"].shape[1]))
+    tg = H.cuda_target(pkg, base)
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    assert np.all(np.isfinite(ll)) and np.all(np.isfinite(g))
+    idx = np.unique(np.concatenate([[0, 1, nc // 2, nc - 2, nc - 1], rng.integers(0, nc, size=7)]))
+    ll_ref, g_ref = H.oracle_batched(base, params[idx])
+    H.assert_parity(ll[idx], g[idx], ll_ref, g_ref, what)
+    # the same chains in a small batch (other block shape / the non-persistent GEMM): same values to rounding
+    sub = np.concatenate([idx, np.arange(100, 140)])
+    ll2, g2 = tg.logdensity_and_gradient_batched(params[sub])
+    H.assert_parity(ll[sub], g[sub], ll2, g2, what + " (vs small batch)")
+
+
 def test_guards_per_chain(pkg):
     """interface.jl:179-182, 222-226: wrong length -> (-Inf, NaN...); a non-finite chain -> (-Inf, 0...) without
     poisoning its neighbours."""
