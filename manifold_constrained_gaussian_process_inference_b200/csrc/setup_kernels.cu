@@ -98,17 +98,24 @@ __global__ void set_diag_kernel(double* __restrict__ A, int n, double v) {   // 
 }
 
 // per batch item: stats[2d] = max |diag|, stats[2d+1] = 1 if any off-diagonal... (used for: pivot tolerance; "all zero" test)
+// (grid = (D, chunks): every block reduces a slice and merges with an atomic max on the bit pattern -- non-negative doubles
+// order like unsigned integers; `out` must be zeroed before the launch)
 __global__ void absmax_kernel(const double* __restrict__ A, int n, int diag_only, double* __restrict__ out) {
     const int d = blockIdx.x;
     const size_t nn = (size_t)n * n;
     __shared__ double red[256];
     double m = 0.0;
-    if (diag_only) { for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(A[d * nn + (size_t)i * n + i])); }
-    else { for (size_t i = threadIdx.x; i < nn; i += blockDim.x) m = fmax(m, fabs(A[d * nn + i])); }
+    const size_t tid = (size_t)blockIdx.y * blockDim.x + threadIdx.x, stride = (size_t)gridDim.y * blockDim.x;
+    if (diag_only) { for (size_t i = tid; i < (size_t)n; i += stride) m = fmax(m, fabs(A[d * nn + i * n + i])); }
+    else { for (size_t i = tid; i < nn; i += stride) m = fmax(m, fabs(A[d * nn + i])); }
     red[threadIdx.x] = m;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
-    if (threadIdx.x == 0) out[d] = red[0];
+    if (threadIdx.x == 0) {
+        const double v = red[0];
+        // (fmax drops NaNs, as in a sequential max of |.|: v is a non-negative number)
+        atomicMax(reinterpret_cast<unsigned long long*>(out + d), (unsigned long long)__double_as_longlong(v));
+    }
 }
 
 // ---------------- K4: diagonal block factorisation + its triangular inverse ----------------
@@ -239,8 +246,10 @@ static GemmArgs gemm_cm(const double* A, bool tA, const double* B, bool tB, doub
 // X = inv(L) by recursive doubling.  T is an n x n work buffer per batch item.
 static int chol_and_inverse(SetupCtx& c, double* A, double* X, double* T, double* d_tinv, double* d_stat, int* d_rep, int NB, int nblk) {
     const int n = c.n, D = c.D;
-    absmax_kernel<<<D, 256, 0, c.st>>>(A, n, 1, d_stat); c.launches++;
+    SCK(cudaMemsetAsync(d_stat, 0, sizeof(double) * D, c.st), "memset stats");
+    absmax_kernel<<<dim3(D, 1), 256, 0, c.st>>>(A, n, 1, d_stat); c.launches++;
     SCK(cudaMemsetAsync(d_rep, 0, sizeof(int) * D, c.st), "memset repaired");
+    const int NBO = (n >= 8 * NB) ? 4 * NB : NB;         // outer panel width
     for (int blk = 0; blk < nblk; ++blk) {
         const int j0 = blk * NB, nb = (n - j0 < NB) ? n - j0 : NB;
         potf2_inv_kernel<<<D, 256, 0, c.st>>>(A, n, j0, nb, d_tinv, blk, nblk, d_stat, d_rep); c.launches++;
@@ -254,13 +263,27 @@ static int chol_and_inverse(SetupCtx& c, double* A, double* X, double* T, double
             g.C = A + (size_t)j0 * n + (j0 + nb); g.rsC = 1; g.csC = n; g.bsC1 = (long long)n * n; g.bsC2 = 0;
             g.M = rem; g.N = nb; g.K = nb; g.nb1 = 1 << 30; g.alpha = 1.0; g.beta = 0.0;
             SCK(launch_gemm(g, D, c.st), "panel gemm"); c.launches++;
-            // trailing: A[j0+nb:, j0+nb:] -= P P^T (lower tiles only)
-            GemmArgs u{};
-            u.A = A + (size_t)j0 * n + (j0 + nb); u.rsA = 1; u.csA = n; u.bsA1 = (long long)n * n;
-            u.B = A + (size_t)j0 * n + (j0 + nb); u.rsB = n; u.csB = 1; u.bsB1 = (long long)n * n;      // B(k,j) = P(j,k)
-            u.C = A + (size_t)(j0 + nb) * n + (j0 + nb); u.rsC = 1; u.csC = n; u.bsC1 = (long long)n * n;
-            u.M = rem; u.N = rem; u.K = nb; u.nb1 = 1 << 30; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
-            SCK(launch_gemm(u, D, c.st), "trailing gemm"); c.launches++;
+            // trailing update, two levels: inside the current outer panel (NBO columns) the update follows every block
+            // (K = nb); the rest of the matrix is updated once per outer panel with K = NBO -- a quarter of the
+            // read-modify-write passes over the trailing matrix, and GEMMs deep enough to run on the tensor pipe
+            // instead of on HBM.  Lower tiles only.
+            const int j1 = j0 + nb, jend = (j0 / NBO + 1) * NBO < n ? (j0 / NBO + 1) * NBO : n, jbeg = (j0 / NBO) * NBO;
+            if (jend > j1) {
+                GemmArgs u{};
+                u.A = A + (size_t)j0 * n + j1; u.rsA = 1; u.csA = n; u.bsA1 = (long long)n * n;
+                u.B = A + (size_t)j0 * n + j1; u.rsB = n; u.csB = 1; u.bsB1 = (long long)n * n;      // B(k,j) = P(j,k)
+                u.C = A + (size_t)j1 * n + j1; u.rsC = 1; u.csC = n; u.bsC1 = (long long)n * n;
+                u.M = rem; u.N = jend - j1; u.K = nb; u.nb1 = 1 << 30; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+                SCK(launch_gemm(u, D, c.st), "trailing gemm (panel)"); c.launches++;
+            }
+            if (j1 == jend && jend < n) {
+                GemmArgs u{};
+                u.A = A + (size_t)jbeg * n + jend; u.rsA = 1; u.csA = n; u.bsA1 = (long long)n * n;
+                u.B = A + (size_t)jbeg * n + jend; u.rsB = n; u.csB = 1; u.bsB1 = (long long)n * n;
+                u.C = A + (size_t)jend * n + jend; u.rsC = 1; u.csC = n; u.bsC1 = (long long)n * n;
+                u.M = n - jend; u.N = n - jend; u.K = jend - jbeg; u.nb1 = 1 << 30; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+                SCK(launch_gemm(u, D, c.st), "trailing gemm (outer)"); c.launches++;
+            }
         }
     }
     zero_upper_kernel<<<ew_grid((size_t)n * n, D), 256, 0, c.st>>>(A, n); c.launches++;
@@ -335,8 +358,10 @@ int gp_setup_device(SetupCtx& c) {
     SETUP_CUDA(cudaGetLastError(), "cov_build_kernel");
     // derivatives "all zero" test of the reference (:299): any dimension with all-zero C' or C'' takes the fallback
     std::vector<double> st(2 * D, 0.0);
-    absmax_kernel<<<D, 256, 0, c.st>>>(Cp, n, 0, d_stat); c.launches++;
-    absmax_kernel<<<D, 256, 0, c.st>>>(Cpp, n, 0, d_stat + D); c.launches++;
+    SETUP_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(double) * 2 * D, c.st), "memset stats");
+    const int abs_chunks = (int)std::min<size_t>(64, ((size_t)n * n + 65535) / 65536);
+    absmax_kernel<<<dim3(D, abs_chunks), 256, 0, c.st>>>(Cp, n, 0, d_stat); c.launches++;
+    absmax_kernel<<<dim3(D, abs_chunks), 256, 0, c.st>>>(Cpp, n, 0, d_stat + D); c.launches++;
     SETUP_CUDA(cudaMemcpyAsync(st.data(), d_stat, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, c.st), "D2H stats");
     SETUP_CUDA(cudaStreamSynchronize(c.st), "sync");
     bool deriv = want_deriv;
