@@ -75,6 +75,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
 
+__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         v1 = (t1 >= 0 && t1 < n) ? base[t1] : 0.0;
     };
     const int NP = NT / 2 + 1;                      // pair-blocks per (view, dimension)
+    const int NPK = (NT + 1) / 2;                   // K~ pairs that hold a tile of the time axis (pairs (2p, 2p+1): no offset)
     constexpr int LE = LAGP + OFF;                  // the K~ pair pb is computed right after e pair pb + LE has entered the window
     const int N2 = (NT - 1 + LAGT) / 2 + 1;         // A2 steps: the output pair (2u - LAGT, +1) reaches tile NT - 1
     auto pair_ok = [&](int pp) { return pp >= 0 && pp < NP; };
@@ -194,18 +197,18 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NP) * BLKP;   // C~
         const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NP) * BLKP;   // K~
         const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NP) * BLKP;   // m~^T
-        // ring B use r: A1 K~ pair r (r < NP); A2 step u = r - NP: C~ pair into ring A's buffer and m~^T pair into ring B's,
+        // ring B use r: A1 K~ pair r (r < NPK); A2 step u = r - NPK: C~ pair into ring A's buffer and m~^T pair into ring B's,
         // both signalled on ring B's barriers (the pointwise warps no longer use ring A then)
         auto issue_b = [&](int r) {
-            if (r < NP) ring_issue(r, ringB, bfull, bempty, ft2 + (size_t)r * BLKP, nullptr, nullptr);
-            else if (r < NP + N2) {
-                const int pc = r - NP - LAGP;
+            if (r < NPK) ring_issue(r, ringB, bfull, bempty, ft2 + (size_t)r * BLKP, nullptr, nullptr);
+            else if (r < NPK + N2) {
+                const int pc = r - NPK - LAGP;
                 ring_issue(r, ringB, bfull, bempty, pair_ok(pc) ? ft3 + (size_t)pc * BLKP : nullptr, ringA, pair_ok(pc) ? ft1 + (size_t)pc * BLKP : nullptr);
             }
         };
         issue_b(0);
-        if (NP > 1) issue_b(1);
-        double acc_eke = 0.0;
+        if (NPK > 1) issue_b(1);
+        double acc_eke = 0.0, acc_xcx = 0.0;
         // ---------------- A1: Ke = K~ e (likelihoods.jl:132); e tiles come from the pointwise warp ----------------
         {
             double ew[W2];
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     }
                     __syncwarp();
                     if (lane == 0) { if (IN) mbar_arrive(q1empty + qs); mbar_arrive(bempty + st); }
-                    if (pb + 2 < NP) issue_b(pb + 2);          // (the A2 uses wait for the block barrier: the pointwise warps may still read ring A)
+                    if (pb + 2 < NPK) issue_b(pb + 2);         // (the A2 uses wait for the block barrier: the pointwise warps may still read ring A)
 #pragma unroll
                     for (int tt = 0; tt < 2; ++tt) {
                         if (tile_ok(2 * pb + tt)) {
@@ -259,16 +262,31 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     if (lane == 0) mbar_arrive(q1empty + qs);
                 }
             };
-            // e pairs arrive for i in [0, NP), K~ pairs are computed for i in [LE, NP + LE): one loop per combination
-            int i = 0;
+            // e pairs arrive for i in [0, NP), K~ pairs are computed for i in [LE, NPK + LE): one loop per combination
+            const int iend = max(NP, NPK + LE);
+            int bp[4] = {0, min(LE, iend), min(NP, iend), min(NPK + LE, iend)};
+            if (bp[1] > bp[2]) { const int t = bp[1]; bp[1] = bp[2]; bp[2] = t; }
+            if (bp[2] > bp[3]) { const int t = bp[2]; bp[2] = bp[3]; bp[3] = t; }
+            if (bp[1] > bp[2]) { const int t = bp[1]; bp[1] = bp[2]; bp[2] = t; }
 #pragma unroll 1
-            for (; i < min(LE, NP); ++i) a1_step(i, std::true_type{}, std::false_type{});
+            for (int seg = 0; seg < 4; ++seg) {
+                const int i0 = bp[seg], i1 = seg < 3 ? bp[seg + 1] : iend;
+                if (i0 >= i1) continue;
+                const bool in = i0 < NP, vb = (i0 >= LE) && (i0 < NPK + LE);
+                if (in && vb) {
 #pragma unroll 1
-            for (; i < LE; ++i) a1_step(i, std::false_type{}, std::false_type{});       // (only when NP < LE)
+                    for (int i = i0; i < i1; ++i) a1_step(i, std::true_type{}, std::true_type{});
+                } else if (in) {
 #pragma unroll 1
-            for (; i < NP; ++i) a1_step(i, std::true_type{}, std::true_type{});
+                    for (int i = i0; i < i1; ++i) a1_step(i, std::true_type{}, std::false_type{});
+                } else if (vb) {
 #pragma unroll 1
-            for (; i < NP + LE; ++i) a1_step(i, std::false_type{}, std::true_type{});
+                    for (int i = i0; i < i1; ++i) a1_step(i, std::false_type{}, std::true_type{});
+                } else {
+#pragma unroll 1
+                    for (int i = i0; i < i1; ++i) a1_step(i, std::false_type{}, std::false_type{});
+                }
+            }
             acc_eke = quad_sum(acc_eke);
         }
         if (a.dbg) tk1 = clock64();
@@ -292,9 +310,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             load_feed(0, nf, nk);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
+            const int uc0 = min(LAGP, N2), uc1 = min(NP + LAGP, N2);
+            // ping-pong partner: the other DMMA warp on this SM sub-partition (warp ^ 4), named barriers 1..8
+            const bool pp_partner = ((warp ^ 4) < ntask) && a.H == 0, pp_first = warp < 4;
+            const int pp_mine = 1 + 2 * (warp & 3) + (pp_first ? 0 : 1), pp_other = 1 + 2 * (warp & 3) + (pp_first ? 1 : 0);
             auto a2_step = [&](int u, auto v_) {
                 constexpr bool V = decltype(v_)::value;
-                const int r = NP + u;
+                const int r = NPK + u;
                 const int st = r % R, qs = u % S;
                 double* xs = xq + (size_t)qs * XS * 32;
 #ifdef MAGI_DBG_WAITS
@@ -311,15 +333,28 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 const double2* frb = reinterpret_cast<const double2*>(ringB + (size_t)st * BLKP) + lane;
                 double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
                 if constexpr (V) {
+                    // The two DMMA warps of an SM sub-partition take turns on the FP64 tensor pipe: while one issues its 48 DMMAs
+                    // (16 clk each, alone on the pipe) the other does its non-DMMA part of the step.  Left alone they run in
+                    // lock-step (same ring barrier releases both), share the pipe during the DMMA blocks and leave it idle
+                    // during the rest.
+                    if (pp_partner) named_barrier(pp_mine, 64);
 #pragma unroll
                     for (int hh = 0; hh < NCH; ++hh) {
                         const double2 fa = fra[hh * 32], fb = frb[hh * 32];
                         dmma884(c[0][0], c[0][1], xw[hh], fa.x);    dmma884(c[1][0], c[1][1], xw[hh + 2], fa.y);     // likelihoods.jl:133
                         dmma884(um[0][0], um[0][1], kw[hh], fb.x);  dmma884(um[1][0], um[1][1], kw[hh + 2], fb.y);   // likelihoods.jl:192
                     }
+                    if (pp_partner && (pp_first || u + 1 < uc1)) named_arrive(pp_other, 64);
                 }
-                xs[0] = c[0][0]; xs[32] = c[0][1]; xs[64] = c[1][0]; xs[96] = c[1][1];
-                xs[128] = um[0][0]; xs[160] = um[0][1]; xs[192] = um[1][0]; xs[224] = um[1][1];
+                // the DMMA warp has slack in this phase: it combines the two products (likelihoods.jl:186,194) and accumulates
+                // x.Cx (:150; x and Cx are both zero outside the time axis), the pointwise warp gets one value per point
+#pragma unroll
+                for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                    for (int pt = 0; pt < 2; ++pt) {
+                        acc_xcx += xw[HB + 2 * tt + pt] * c[tt][pt];
+                        xs[(2 * tt + pt) * 32] = um[tt][pt] * inv_b1 - c[tt][pt] * inv_b2;
+                    }
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(q2full + qs); mbar_arrive(bempty + st); }
                 issue_b(r + 2);
@@ -328,8 +363,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
             };
-            issue_b(NP); issue_b(NP + 1);                        // (after the block barrier: ring A's buffer is free now)
-            const int uc0 = min(LAGP, N2), uc1 = min(NP + LAGP, N2);
+            issue_b(NPK); issue_b(NPK + 1);                      // (after the block barrier: ring A's buffer is free now)
+            if (pp_partner && !pp_first && uc1 > uc0) named_arrive(pp_other, 64);      // the first warp of the pair may start
             int u = 0;
 #pragma unroll 1
             for (; u < uc0; ++u) a2_step(u, std::false_type{});
@@ -340,7 +375,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         }
         if (a.dbg) tk3 = clock64();
         __syncthreads();                                     // the queues are dead: `red` may overwrite them
-        if (q == 0) red[((size_t)(g * 8 + gid) * D + d) * RED + 0] = acc_eke;
+        acc_xcx = quad_sum(acc_xcx);
+        if (q == 0) { red[((size_t)(g * 8 + gid) * D + d) * RED + 0] = acc_eke; red[((size_t)(g * 8 + gid) * D + d) * RED + 1] = acc_xcx; }
     };
 
     // =========================== pointwise warp ===========================
@@ -417,7 +453,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             for (; u < NP + LAGP; ++u) a1_step(u, std::true_type{});
         }
         // A2 prologue that does not depend on the Ke scratch
-        double acc_xcx = 0.0, acc_sse = 0.0;
+        double acc_sse = 0.0;
         double gth[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) gth[i] = 0.0;
@@ -504,7 +540,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #ifdef MAGI_DBG_WAITS
             wq += clock64() - w0;
 #endif
-            const double cxv[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}}, mtv[2][2] = {{xs[128], xs[160]}, {xs[192], xs[224]}};
+            const double gb[2][2] = {{xs[0], xs[32]}, {xs[64], xs[96]}};      // m~^T Ke / beta1 - C~ x / beta2 at this lane's four points
             __syncwarp();
             if (lane == 0) mbar_arrive(q2empty + qs);            // the stage is free again while the gradient is computed
 #pragma unroll
@@ -513,19 +549,15 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 for (int pt = 0; pt < 2; ++pt) {
                     const int t = 8 * (Jc + tt) + q + 4 * pt;
                     const bool valid = INTERIOR || (tile_ok(Jc + tt) && t < n);
-                    const double cx = cxv[tt][pt], mt = mtv[tt][pt];
                     const double* xv = xa[tt][pt];
                     const double* w = wv[tt][pt];
                     const double xdv = xv[d], wd = valid ? w[d] : 0.0;
                     const double y = yv[tt][pt];
                     const bool fin = valid && isfinite(y);         // likelihoods.jl:123
                     const double e0 = fin ? xdv - y : 0.0;
-                    double gv = -(e0 * obs_scale);                 // likelihoods.jl:179 (e0 = 0 when the observation is missing)
-                    gv -= cx * inv_b2;                             // likelihoods.jl:186
-                    gv += mt * inv_b1;                             // likelihoods.jl:194
+                    double gv = gb[tt][pt] - e0 * obs_scale;       // likelihoods.jl:179 (e0 = 0 when the observation is missing), :186, :194
                     M::jx_col_sub(d, xv, th, w, gv);               // likelihoods.jl:214-216
                     M::jth_row_sub(d, xv, th, wd, gth);            // likelihoods.jl:219-221
-                    acc_xcx += valid ? xdv * cx : 0.0;             // likelihoods.jl:150
                     acc_sse += e0 * e0;                            // likelihoods.jl:139,234
                     bad |= valid && !isfinite(gv);
                     if (valid && gout != nullptr) gout[t] = gv;
@@ -541,7 +573,6 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll 1
             for (; u < N2; ++u) a2_step(u, std::false_type{});
         }
-        acc_xcx = quad_sum(acc_xcx);
         acc_sse = quad_sum(acc_sse);
 #pragma unroll
         for (int i = 0; i < K; ++i) gth[i] = quad_sum(gth[i]);
@@ -549,7 +580,6 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         __syncthreads();                                     // the queues are dead: `red` may overwrite them
         if (q == 0) {
             double* r = red + ((size_t)(g * 8 + gid) * D + d) * RED;
-            r[1] = acc_xcx;
             r[2] = acc_sse;
             r[3] = ((badm >> (gid * 4)) & 0xfu) ? 1.0 : 0.0;
 #pragma unroll

@@ -203,6 +203,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     a.fragtab = h->d_fragtab; a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
     for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
     a.scratch = h->d_scratch;
+    { static const bool no_pp = getenv("MAGI_NO_PINGPONG") != nullptr; a.H = no_pp ? 1 : 0; }   // H != 0 disables the DMMA ping-pong (A/B measurement)
     a.dbg = nullptr;
     static const bool dbg_clocks = getenv("MAGI_DBG_CLOCKS") != nullptr;
     long long* d_dbg = nullptr;
