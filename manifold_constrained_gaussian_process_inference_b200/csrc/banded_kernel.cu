@@ -109,7 +109,7 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, 
     const bool force_global = getenv("MAGI_FORCE_GLOBAL_SCRATCH") != nullptr;
     // rings [D][kRingStages][4 blocks] + queues [G*D tasks][kXStages][kXSlots][32 lanes] + mbarriers (banded_kernel.cuh);
     // the per-chain reduction area aliases the queues
-    constexpr int R = 3, S = 3, XS = 8;
+    constexpr int R = 3, S = 3, XS = 4;
     auto fixed_bytes = [&](int g) { return ((size_t)D * R * 4 * NCH * 32 + (size_t)g * D * S * XS * 32 + 4 * R * D + 4 * S * g * D) * sizeof(double); };
     // As many chain-groups per block as fit 16 warps (2 warps per task); for long time axes the Ke scratch of that many
     // groups does not fit shared memory and goes to global memory (L2-resident): on LV n=1281 G=4 with L2 scratch ran in

@@ -103,7 +103,7 @@ template <int D, class F> __device__ __forceinline__ void dispatch_dim(int d, F&
 // Fragment blocks arrive by TMA bulk copy into a kRingStages-deep ring per dimension, shared by the G DMMA warps of that
 // dimension: full[stage] (expect_tx) / empty[stage] (G arrivals) mbarriers, issued two steps ahead by one elected thread,
 // running straight through the A1 -> A2 boundary; one 16-byte LDS per two chunks.
-constexpr int kXStages = 3, kRingStages = 3, kXSlots = 8;
+constexpr int kXStages = 3, kRingStages = 3, kXSlots = 4;
 
 template <int MODEL, int HB>
 __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs a) {
