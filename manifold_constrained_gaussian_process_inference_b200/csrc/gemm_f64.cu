@@ -89,13 +89,19 @@ __global__ void __launch_bounds__(256) gemm_f64_dmma_kernel(const GemmArgs g) {
             }
 }
 
-// ---- large-tile kernel: 128 x 128 x 32 block tiles, 16 warps (4 x 4, warp tile 32 x 32 = 4 x 4 DMMA tiles, 16 independent
-// accumulate chains), 3-stage cp.async pipeline (8-byte copies with zero fill: the operands are arbitrary strided views, so
+// ---- large-tile kernel: 128 x 128 x 16 block tiles, 16 warps (4 x 4, warp tile 32 x 32 = 4 x 4 DMMA tiles, 16 independent
+// accumulate chains), 4-stage cp.async pipeline (8-byte copies with zero fill: the operands are arbitrary strided views, so
 // wider copies are not generally aligned), one block barrier per k-tile.  Each operand tile is staged in the direction it is
 // contiguous in global memory (template flags) with a leading dimension that makes the DMMA fragment loads conflict-free:
 //   m (n)-contiguous: S[k][m], LD = 132  -> fragment word banks 8q + 2 gid      k-contiguous: S[m][k], LD = BK + 4 -> 8 gid + 2q
 // Per k4 step a warp issues 8 LDS.64 for 16 DMMAs.  Used for the dense-mode (band = n-1) operators and the large setup GEMMs.
-constexpr int BG_BM = 128, BG_BN = 128, BG_BK = 32, BG_ST = 3, BG_LDM = 132, BG_LDK = BG_BK + 4;
+#ifndef MAGI_GEMM_BK
+#define MAGI_GEMM_BK 16
+#endif
+#ifndef MAGI_GEMM_ST
+#define MAGI_GEMM_ST 4
+#endif
+constexpr int BG_BM = 128, BG_BN = 128, BG_BK = MAGI_GEMM_BK, BG_ST = MAGI_GEMM_ST, BG_LDM = 132, BG_LDK = BG_BK + 4;
 constexpr int BG_CP = BG_BM * BG_BK / 512;        // 8-byte copies per thread, operand and k-tile
 constexpr int BG_TILE = (BG_BK * BG_LDM > BG_BM * BG_LDK) ? BG_BK * BG_LDM : BG_BM * BG_LDK;   // doubles per operand stage
 
