@@ -280,6 +280,7 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         g.B = B; g.rsB = rsB; g.csB = csB; g.bsB1 = bsB; g.bsB2 = 0;
         g.C = C; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = 0;
         g.M = n; g.N = n_chains; g.K = n; g.nb1 = 1 << 30; g.alpha = 1.0; g.beta = 0.0;
+        g.a_band = (h->b < n - 1) ? h->b : 0;       // band-truncated operators: only the k-tiles that meet the band are multiplied
         g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch;
         if (g.sk_epoch == 0) g.sk_epoch = ++h->sk_epoch;
         cudaError_t e = launch_gemm(g, D, st);

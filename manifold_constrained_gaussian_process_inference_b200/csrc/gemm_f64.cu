@@ -23,9 +23,14 @@ __global__ void __launch_bounds__(256) gemm_f64_dmma_kernel(const GemmArgs g) {
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    int k_begin = 0;
+    int k_begin = 0, k_end = g.K;
     if (g.k_lo_from_tile) { int t = m0 > n0 ? m0 : n0; k_begin = (t / GEMM_BK) * GEMM_BK; }
-    const int nkt = (g.K - k_begin + GEMM_BK - 1) / GEMM_BK;
+    if (g.a_band > 0) {
+        const int lo = m0 - g.a_band, hi = m0 + GEMM_BM + g.a_band;
+        if (lo > k_begin) k_begin = (lo / GEMM_BK) * GEMM_BK;
+        if (hi < k_end) k_end = hi;
+    }
+    const int nkt = k_end > k_begin ? (k_end - k_begin + GEMM_BK - 1) / GEMM_BK : 0;
     double ra[4], rb[4];
     auto gload = [&](int kt) {
         const int k0 = k_begin + kt * GEMM_BK;
@@ -215,9 +220,14 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_big_kernel(const GemmArg
     const double* A = g.A + z1 * g.bsA1 + z2 * g.bsA2;
     const double* B = g.B + z1 * g.bsB1 + z2 * g.bsB2;
     double* C = g.C + z1 * g.bsC1 + z2 * g.bsC2;
-    int k_begin = 0;
+    int k_begin = 0, k_end = g.K;
     if (g.k_lo_from_tile) { int t = m0 > n0 ? m0 : n0; k_begin = (t / BG_BK) * BG_BK; }
-    const int nkt = (g.K - k_begin + BG_BK - 1) / BG_BK;
+    if (g.a_band > 0) {
+        const int lo = m0 - g.a_band, hi = m0 + BG_BM + g.a_band;
+        if (lo > k_begin) k_begin = (lo / BG_BK) * BG_BK;
+        if (hi < k_end) k_end = hi;
+    }
+    const int nkt = k_end > k_begin ? (k_end - k_begin + BG_BK - 1) / BG_BK : 0;
     double acc[4][4][2];
     big_mainloop<AK, BKC>(g, A, B, m0, n0, k_begin, 0, nkt, As, Bs, acc);
     big_store(g, C, m0, n0, acc);
@@ -363,7 +373,7 @@ cudaError_t launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
         const int m_rem = g.M % BG_BM;
         const bool cut = (m_rem > 0 && m_rem <= 16 && g.M > BG_BM);
         const int tm = cut ? g.M / BG_BM : (g.M + BG_BM - 1) / BG_BM, tn = (g.N + BG_BN - 1) / BG_BN;
-        if (!no_streamk && g.sk_work && g.sk_flags && !g.lower_only && !g.k_lo_from_tile && sm_count <= kStreamKSlots - 1 &&
+        if (!no_streamk && g.sk_work && g.sk_flags && !g.lower_only && !g.k_lo_from_tile && g.a_band == 0 && sm_count <= kStreamKSlots - 1 &&
             (long long)tm * tn * batch >= sm_count) {
             GemmArgs m = g; if (cut) m.M = tm * BG_BM;
             cudaError_t e = ak ? (bkc ? launch_streamk<true, true>(m, tm, tn, batch, sm_count, st) : launch_streamk<true, false>(m, tm, tn, batch, sm_count, st))

@@ -15,6 +15,7 @@ struct GemmArgs {
     double alpha, beta;
     int lower_only;       // skip output tiles that lie strictly above the diagonal (symmetric updates)
     int k_lo_from_tile;   // 1: A and B are lower-triangular-structured such that k < max(tile row0, tile col0) contributes 0
+    int a_band = 0;       // > 0: A(m, k) is zero for |m - k| > a_band (band-truncated operator): k-tiles outside the band are skipped
     // optional stream-K work space (see gemm_f64.cu): partial tiles [kStreamKSlots][128 x 128] and one flag per slot; the caller
     // owns both, zero-initialises the flags once and passes a fresh non-zero epoch per launch.  Null: data-parallel tiles only.
     double* sk_work = nullptr;
