@@ -30,6 +30,7 @@ struct HmcState {
     double *acc_sum = nullptr;                                           // per-chain sum of acceptance probabilities
     int *n_div = nullptr;
     double *wsum = nullptr, *wsq = nullptr;                              // pooled window accumulators [P]
+    double *wpart = nullptr;                                             // [kWinSlices][2][P] partial sums of one iteration
     long long wcount = 0;
     double *draws = nullptr; long long draws_cap = 0, n_draws = 0;       // [n_draws][n_chains][k + D + 1]
     double *xsum = nullptr; long long xsum_count = 0;                    // per-chain running sum of vec(X) over kept draws
@@ -87,8 +88,16 @@ __global__ void hmc_begin_kernel(HmcState s, int P) {
             }
         }
     }
+    // ordered reduction (no atomics: the Hamiltonian, hence every accept / reject decision, is reproducible bit for bit)
+    __shared__ double sh[8];
     for (int o = 16; o > 0; o >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s.h0[c], kin);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = kin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double k = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) k += sh[i];
+        s.h0[c] += k;
+    }
 }
 
 // h0[c] = -ll[c] (before the kinetic energy is accumulated); ll0 snapshot
@@ -168,13 +177,6 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
         if (threadIdx.x == 0) s.ll[c] = s.ll0[c];
     }
     __syncthreads();
-    if (f.accumulate_window) {
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            const double q = s.q[base + i];
-            atomicAdd(&s.wsum[i], q);
-            atomicAdd(&s.wsq[i], q * q);
-        }
-    }
     if (f.accumulate_x) for (int i = threadIdx.x; i < f.nD; i += blockDim.x) s.xsum[(size_t)c * f.nD + i] += s.q[base + i];
     if (f.store && threadIdx.x < f.n_draw_cols) {
         double* out = s.draws + ((size_t)s.n_draws * s.n_chains + c) * f.n_draw_cols;
@@ -187,6 +189,26 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
         } else v = s.ll[c];                                                           // lp
         out[j] = v;
     }
+}
+
+// pooled window statistics without atomics: partial sums over fixed slices of chains, then the slices in order
+constexpr int kWinSlices = 64;
+__global__ void hmc_window_partial_kernel(HmcState s, int P, double* __restrict__ part) {      // grid (ceil(P/128), kWinSlices)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int per = (s.n_chains + kWinSlices - 1) / kWinSlices;
+    const int c0 = blockIdx.y * per, c1 = min(s.n_chains, c0 + per);
+    double a = 0.0, b = 0.0;
+    for (int c = c0; c < c1; ++c) { const double q = s.q[(size_t)c * P + i]; a += q; b += q * q; }
+    part[(size_t)blockIdx.y * 2 * P + i] = a;
+    part[(size_t)blockIdx.y * 2 * P + P + i] = b;
+}
+__global__ void hmc_window_merge_kernel(HmcState s, int P, const double* __restrict__ part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < kWinSlices; ++k) { a += part[(size_t)k * 2 * P + i]; b += part[(size_t)k * 2 * P + P + i]; }
+    s.wsum[i] += a; s.wsq[i] += b;
 }
 
 __global__ void hmc_window_finish_kernel(HmcState s, int P, double count, int reset_only) {
@@ -220,7 +242,7 @@ __global__ void fill_double_kernel(double* p, size_t nel, double v) {
 void hmc_free(magi_handle* h) {
     HmcState* s = (HmcState*)h->hmc;
     if (!s) return;
-    double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->draws, s->xsum};
+    double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->wpart, s->draws, s->xsum};
     for (double* p : ptrs) if (p) cudaFree(p);
     if (s->n_div) cudaFree(s->n_div);
     delete s;
@@ -251,6 +273,7 @@ extern "C" int magi_hmc_init(magi_handle* h, int n_chains, const double* params0
     HCK(cudaMalloc(&s->minv, sizeof(double) * P), "cudaMalloc minv");
     HCK(cudaMalloc(&s->wsum, sizeof(double) * P), "cudaMalloc wsum");
     HCK(cudaMalloc(&s->wsq, sizeof(double) * P), "cudaMalloc wsq");
+    HCK(cudaMalloc(&s->wpart, sizeof(double) * 2 * P * 64), "cudaMalloc window partial sums");
     HCK(cudaMalloc(&s->xsum, sizeof(double) * (size_t)n_chains * h->n * h->D), "cudaMalloc xsum");
     cudaStream_t st = h->stream;
     HCK(cudaMemcpyAsync(s->q, params0, sizeof(double) * NP, cudaMemcpyHostToDevice, st), "H2D initial state");
@@ -298,7 +321,7 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
     f.delta = target_accept; f.mu_scale = 10.0;
     for (int it = 0; it < n_iter; ++it) {
         hmc_prep_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s);
-        hmc_begin_kernel<<<egrid, 128, 0, st>>>(*s, P);
+        hmc_begin_kernel<<<dim3(nc, 1), 256, 0, st>>>(*s, P);      // one block per chain (ordered reduction of the kinetic energy)
         h->launches += 2;
         for (int l = 0; l < n_leapfrog; ++l) {
             int rc = eval_dev(h, nc, s->q, P, s->ll, s->g, st);
@@ -310,6 +333,11 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
         f.store = store_draws; f.accumulate_window = in_slow ? 1 : 0; f.accumulate_x = store_draws ? 1 : 0;
         hmc_finish_kernel<<<nc, 256, 0, st>>>(*s, P, f);
         h->launches++;
+        if (in_slow) {
+            hmc_window_partial_kernel<<<dim3((P + 127) / 128, kWinSlices), 128, 0, st>>>(*s, P, s->wpart);
+            hmc_window_merge_kernel<<<(P + 127) / 128, 128, 0, st>>>(*s, P, s->wpart);
+            h->launches += 2;
+        }
         s->iter++;
         if (store_draws) { s->n_draws++; s->xsum_count++; }
         s->acc_count++;

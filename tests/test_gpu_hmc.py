@@ -87,6 +87,22 @@ def test_hmc_is_invariant_to_sharding(pkg):
     assert np.array_equal(full[:, :8], a) and np.array_equal(full[:, 8:], b)
 
 
+def test_hmc_is_reproducible_bit_for_bit(pkg):
+    """Same seed, same draws -- including the warm-up (dual averaging, pooled windowed metric): the kinetic energy and the
+    window statistics are reduced in a fixed order (no atomics), at a size where several warps and blocks contribute."""
+    prob = H.make_problem(n=201, T=20.0, b=20, n_chains=8, seed=11, obs_every=5)
+    rng = np.random.default_rng(3)
+    params = np.repeat(prob["params"], 24, axis=0) + 1e-3 * rng.normal(size=(192, prob["params"].shape[1]))
+    def run():
+        tg = H.cuda_target(pkg, prob)
+        chain, st = pkg.run_hmc_sampler(tg, params, n_samples=40, n_adapts=30, initial_step_size=0.002, n_leapfrog=5, seed=5)
+        return chain, st
+    c1, s1 = run()
+    c2, s2 = run()
+    assert np.array_equal(c1, c2)
+    assert np.array_equal(s1["step_size"], s2["step_size"]) and np.array_equal(s1["inverse_metric"], s2["inverse_metric"])
+
+
 def test_hmc_energy_conservation_and_reversibility_proxy(pkg):
     """With a tiny step the acceptance probability must be ~1 (the leapfrog integrates the gradient the kernel returns)."""
     prob = H.make_problem(n=41, T=8.0, b=6, n_chains=32, seed=2)
