@@ -115,7 +115,7 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, 
     // groups does not fit shared memory and goes to global memory (L2-resident): on LV n=1281 G=4 with L2 scratch ran in
     // 0.27 ms against 0.45 ms for G=1 with shared-memory scratch.
     for (int g = gmax; g >= 1; --g) {
-        if (2 * g * D > 16) continue;
+        if (2 * g * D > 16 || (g & (g - 1)) != 0) continue;      // powers of two only (the ring producer rotates with r & (G - 1))
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0 && force_global) continue;
             size_t red = 0;   // aliased

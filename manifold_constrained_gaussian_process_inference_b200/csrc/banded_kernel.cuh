@@ -12,8 +12,8 @@
 // (lane (gid,q) owns times 8J+q and 8J+q+4 of tile J) makes the C fragment of one product directly usable as the A
 // fragment of the next.
 //
-//   phase A1:  mx = m~ x_d;  e = f_d(x, theta) - mx;  Ke = K~ e  -> Ke scratch; sum e.Ke
-//   phase A2:  Cx = C~ x_d;  mt = m~^T Ke_d;  pointwise gradient incl. the ODE Jacobian terms, which need Ke of ALL
+//   phase A1:  mx = m~ x_d;  e = f_d(x, theta) - mx (pointwise warps);  Ke = K~ e  -> Ke scratch; sum e.Ke (DMMA warps)
+//   phase A2:  Cx = C~ x_d;  mt = m~^T Ke_d (DMMA warps);  pointwise gradient incl. the ODE Jacobian terms, which need Ke of ALL
 //              dimensions at the same time point (hence the block-wide barrier in between)
 //   final (per chain):  log-likelihood assembly in the reference's term order, sigma gradient, log-sigma transform and the
 //              per-chain -Inf / zero-gradient guards (interface.jl:179-264).
@@ -91,18 +91,20 @@ template <int D, class F> __device__ __forceinline__ void dispatch_dim(int d, F&
     if constexpr (D >= 5) { if (d == 4) { f(std::integral_constant<int, 4>{}); return; } }
 }
 
-// Warp-specialised K1 (v10).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
-// warp ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers.  The C warp owns the operand windows (x, e / Ke
-// in registers, sliding two 8-time tiles per step) and issues fragment LDS, window moves, DMMAs and its own (prefetched) x
-// loads; the P warp does all scalar FP64 work (ODE right-hand side, Jacobian terms, reductions, gradient stores).  All
-// hand-offs are ONE-DIRECTIONAL queues of kXStages stages in shared memory (a "full" and an "empty" mbarrier per stage), so
-// neither warp ever waits for a round trip through the other:
-//   A1  P(u): f(x, theta) at tiles (Ja, Ja+1) -> queue (P runs ahead)      C(u): mx = m~ x, e = f - mx straight into the e
-//       window (next step), Ke tiles (Jb, Jb+1) = K~ e -> Ke scratch, sum e.Ke
-//   A2  C(u): Cx, m~^T Ke tiles (Jc, Jc+1) -> queue (C runs ahead)         P(u): gradient incl. Jacobian terms, stores, sums
-// Fragment blocks arrive by TMA bulk copy into a kRingStages-deep ring per dimension, shared by the G DMMA warps of that
-// dimension: full[stage] (expect_tx) / empty[stage] (G arrivals) mbarriers, issued two steps ahead by one elected thread,
-// running straight through the A1 -> A2 boundary; one 16-byte LDS per two chunks.
+// Warp-specialised K1 (v12).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
+// warp ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers, one block per SM.  Operand windows (x, e, Ke)
+// live in registers and slide two 8-time tiles per step.  All hand-offs are ONE-DIRECTIONAL queues of kXStages stages in
+// shared memory (a "full" and an "empty" mbarrier per stage), so neither warp waits for a round trip through the other:
+//   A1  P(u): mx = m~ x (x window), e = f(x, theta) - mx at tiles (Ja, Ja+1) -> queue (P runs ahead)
+//       C(i): e window <- queue; Ke pair = K~ e -> Ke scratch, sum e.Ke            (four DMMA-issuing warps per sub-partition)
+//   A2  C(u): Cx, m~^T Ke tiles (Jc, Jc+1) from the x and Ke windows, combined; x.Cx -> queue (C runs ahead); the two DMMA
+//       warps of an SM sub-partition take turns on the tensor pipe (named-barrier ping-pong)
+//       P(u): gradient incl. Jacobian terms, stores, sums (predicate-free variant for steps inside the time axis)
+// Fragment pair-blocks arrive by TMA bulk copy into two kRingStages-deep rings per dimension (ring A: m~ for the P warps in A1,
+// C~ in A2; ring B: K~ in A1, m~^T in A2, for the C warps): full[stage] (expect_tx) / empty[stage] (G arrivals) mbarriers,
+// issued two uses ahead by an elected thread of the consumer warp whose turn it is (the duty rotates); one 16-byte LDS feeds
+// the same chunk of both tiles of a pair, i.e. two independent accumulate chains.
+// Measured behaviour, what limits it and every variant tried: DESIGN.md section 4, profiles/README.md.
 constexpr int kXStages = 3, kRingStages = 3, kXSlots = 4;
 
 template <int MODEL, int HB>
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     // dimension (use r is issued by warp g = r mod G), so that no warp is systematically slower than the ones it shares the
     // ring with.  No proxy fence: the stage was only READ through the generic proxy, before the consumers' arrivals.
     auto ring_issue = [&](int r, double* buf, unsigned long long* full, unsigned long long* empty, const double* src, double* buf2, const double* src2) {
-        if ((r % G) != g) return;                                         // warp-uniform
+        if ((r & (G - 1)) != g) return;                                   // warp-uniform (G is a power of two: banded_pick_config)
         if (lane == 0) {
             const int st = r % R;
             if (r >= R) mbar_wait(empty + st, ((r / R) - 1) & 1);
