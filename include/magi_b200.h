@@ -144,6 +144,10 @@ int magi_gp_nlml_batched(int kernel_id, int n, const double* t, const double* y,
  * chains are sharded over GPUs. */
 int magi_hmc_init(magi_handle* h, int n_chains, const double* params0 /* P x n_chains */, unsigned long long seed,
                   double step_size0, long long chain_id_offset);
+/* multi-rank runs (chains sharded over GPUs): total chain count and an in-place sum-over-ranks callback
+ * (device pointer, number of doubles, cudaStream_t, user) for the pooled window statistics of the warm-up; returns 0 on success */
+typedef int (*magi_allreduce_fn)(void* dev_ptr, long long n_doubles, void* stream, void* user);
+int magi_hmc_set_global(magi_handle* h, long long n_chains_total, magi_allreduce_fn allreduce, void* user);
 int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream);
 int magi_hmc_reset_stats(magi_handle* h);
 int magi_hmc_get_state(magi_handle* h, double* params /* P x n_chains or NULL */, double* ll /* n_chains or NULL */);

@@ -36,6 +36,9 @@ LAYOUT_CHAIN_CONTIGUOUS = 0
 
 _lib = None
 
+# int (*magi_allreduce_fn)(void* dev_ptr, long long n_doubles, void* stream, void* user)  -- include/magi_b200.h
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p)
+
 # every symbol include/magi_b200.h declares (tests check the .so exports each of them)
 EXPORTED = [
     "magi_last_error", "magi_version", "magi_create", "magi_destroy", "magi_dimension", "magi_capabilities_order",
@@ -43,6 +46,7 @@ EXPORTED = [
     "magi_logdensity_and_gradient_batched_dev", "magi_get_matrix", "magi_set_band_tables", "magi_setup_status",
     "magi_launch_count", "magi_gp_covariances", "magi_gp_nlml_batched", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
     "magi_hmc_get_state", "magi_hmc_get_draws", "magi_hmc_draws_dev", "magi_hmc_get_stats", "magi_hmc_grad_evals",
+    "magi_hmc_set_global",
 ]
 
 
@@ -95,6 +99,8 @@ def _optional(L):
         L.magi_hmc_get_stats.argtypes = [vp, dp, dp, c_int_p, dp, dp]
         L.magi_hmc_grad_evals.argtypes = [vp]
         L.magi_hmc_grad_evals.restype = ll
+    if hasattr(L, "magi_hmc_set_global"):
+        L.magi_hmc_set_global.argtypes = [vp, ctypes.c_longlong, ALLREDUCE_FN, vp]
 
 
 def check(rc):

@@ -30,7 +30,10 @@ struct HmcState {
     double *acc_sum = nullptr;                                           // per-chain sum of acceptance probabilities
     int *n_div = nullptr;
     double *wsum = nullptr, *wsq = nullptr;                              // pooled window accumulators [P]
-    double *wpart = nullptr;                                             // [kWinSlices][2][P] partial sums of one iteration
+    double *wpart = nullptr;                                             // [kWinSlices][2][P] per-slice sums of the current window
+    long long n_chains_total = 0;                                        // chains of ALL ranks (slices are defined on global chain ids)
+    int (*allreduce)(void*, long long, void*, void*) = nullptr;          // optional in-place sum over ranks (magi_hmc_set_global)
+    void* allreduce_user = nullptr;
     long long wcount = 0;
     double *draws = nullptr; long long draws_cap = 0, n_draws = 0;       // [n_draws][n_chains][k + D + 1]
     double *xsum = nullptr; long long xsum_count = 0;                    // per-chain running sum of vec(X) over kept draws
@@ -191,24 +194,34 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
     }
 }
 
-// pooled window statistics without atomics: partial sums over fixed slices of chains, then the slices in order
+// Pooled window statistics without atomics, identical for every sharding of the chains: the GLOBAL chain ids are cut into
+// kWinSlices fixed slices; a slice's running sums add this iteration's chains in ascending order; at the end of a window the
+// slices are (optionally summed over ranks -- every slice lives on one rank, the others add exact zeros -- and) merged in
+// slice order.
 constexpr int kWinSlices = 64;
 __global__ void hmc_window_partial_kernel(HmcState s, int P, double* __restrict__ part) {      // grid (ceil(P/128), kWinSlices)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const int per = (s.n_chains + kWinSlices - 1) / kWinSlices;
-    const int c0 = blockIdx.y * per, c1 = min(s.n_chains, c0 + per);
+    const long long per = (s.n_chains_total + kWinSlices - 1) / kWinSlices;
+    long long c0 = (long long)blockIdx.y * per - s.chain_offset, c1 = c0 + per;
+    if (c0 < 0) c0 = 0;
+    if (c1 > s.n_chains) c1 = s.n_chains;
     double a = 0.0, b = 0.0;
-    for (int c = c0; c < c1; ++c) { const double q = s.q[(size_t)c * P + i]; a += q; b += q * q; }
-    part[(size_t)blockIdx.y * 2 * P + i] = a;
-    part[(size_t)blockIdx.y * 2 * P + P + i] = b;
+    for (long long c = c0; c < c1; ++c) { const double q = s.q[(size_t)c * P + i]; a += q; b += q * q; }
+    if (c1 > c0) {
+        part[(size_t)blockIdx.y * 2 * P + i] += a;
+        part[(size_t)blockIdx.y * 2 * P + P + i] += b;
+    }
 }
-__global__ void hmc_window_merge_kernel(HmcState s, int P, const double* __restrict__ part) {
+__global__ void hmc_window_merge_kernel(HmcState s, int P, double* __restrict__ part) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < kWinSlices; ++k) { a += part[(size_t)k * 2 * P + i]; b += part[(size_t)k * 2 * P + P + i]; }
-    s.wsum[i] += a; s.wsq[i] += b;
+    for (int k = 0; k < kWinSlices; ++k) {
+        a += part[(size_t)k * 2 * P + i]; b += part[(size_t)k * 2 * P + P + i];
+        part[(size_t)k * 2 * P + i] = 0.0; part[(size_t)k * 2 * P + P + i] = 0.0;
+    }
+    s.wsum[i] = a; s.wsq[i] = b;
 }
 
 __global__ void hmc_window_finish_kernel(HmcState s, int P, double count, int reset_only) {
@@ -273,7 +286,9 @@ extern "C" int magi_hmc_init(magi_handle* h, int n_chains, const double* params0
     HCK(cudaMalloc(&s->minv, sizeof(double) * P), "cudaMalloc minv");
     HCK(cudaMalloc(&s->wsum, sizeof(double) * P), "cudaMalloc wsum");
     HCK(cudaMalloc(&s->wsq, sizeof(double) * P), "cudaMalloc wsq");
-    HCK(cudaMalloc(&s->wpart, sizeof(double) * 2 * P * 64), "cudaMalloc window partial sums");
+    HCK(cudaMalloc(&s->wpart, sizeof(double) * 2 * P * kWinSlices), "cudaMalloc window slice sums");
+    HCK(cudaMemsetAsync(s->wpart, 0, sizeof(double) * 2 * P * kWinSlices, h->stream), "memset");
+    s->n_chains_total = n_chains;
     HCK(cudaMalloc(&s->xsum, sizeof(double) * (size_t)n_chains * h->n * h->D), "cudaMalloc xsum");
     cudaStream_t st = h->stream;
     HCK(cudaMemcpyAsync(s->q, params0, sizeof(double) * NP, cudaMemcpyHostToDevice, st), "H2D initial state");
@@ -290,6 +305,18 @@ extern "C" int magi_hmc_init(magi_handle* h, int n_chains, const double* params0
     if (rc) return rc;
     s->grad_evals += n_chains;
     HCK(cudaStreamSynchronize(st), "hmc init sync");
+    return MAGI_OK;
+}
+
+// Multi-rank runs: the total number of chains over all ranks (the pooled metric is a statistic of ALL chains) and an in-place
+// sum-over-ranks callback for the window statistics, called on the sampler's stream at the end of every adaptation window.
+// With both set, warm-up and sampling are bit-identical to a one-rank run over the same global chains whenever the shard
+// boundaries fall on slice boundaries (n_chains_total / 64 chains per slice).  Call after magi_hmc_init.
+extern "C" int magi_hmc_set_global(magi_handle* h, long long n_chains_total, int (*allreduce)(void*, long long, void*, void*), void* user) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_set_global: call magi_hmc_init first");
+    HmcState* s = (HmcState*)h->hmc;
+    if (n_chains_total < s->n_chains + s->chain_offset) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_set_global: n_chains_total is smaller than this rank's last chain id");
+    s->n_chains_total = n_chains_total; s->allreduce = allreduce; s->allreduce_user = user;
     return MAGI_OK;
 }
 
@@ -335,15 +362,20 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
         h->launches++;
         if (in_slow) {
             hmc_window_partial_kernel<<<dim3((P + 127) / 128, kWinSlices), 128, 0, st>>>(*s, P, s->wpart);
-            hmc_window_merge_kernel<<<(P + 127) / 128, 128, 0, st>>>(*s, P, s->wpart);
-            h->launches += 2;
+            h->launches++;
         }
         s->iter++;
         if (store_draws) { s->n_draws++; s->xsum_count++; }
         s->acc_count++;
         if (in_slow) {
-            s->wcount += nc;
+            s->wcount += s->n_chains_total;
             if (it + 1 == win_end) {
+                if (s->allreduce) {                               // sum of the per-slice sums over the ranks (in place, on this stream)
+                    int rc = s->allreduce(s->wpart, (long long)kWinSlices * 2 * P, (void*)st, s->allreduce_user);
+                    if (rc) return set_error(MAGI_ERR_CUDA, "magi_hmc_run: the window all-reduce callback failed");
+                }
+                hmc_window_merge_kernel<<<(P + 127) / 128, 128, 0, st>>>(*s, P, s->wpart);
+                h->launches++;
                 hmc_window_finish_kernel<<<(P + 255) / 256, 256, 0, st>>>(*s, P, (double)s->wcount, 0);
                 hmc_restart_da_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s, 0);
                 h->launches += 2;

@@ -50,3 +50,31 @@ def device_draws_as_tensor(target):
     holder = _Holder()
     holder.__cuda_array_interface__ = {"shape": (ns, nc, ncol), "typestr": "<f8", "data": (ptr, False), "version": 2}
     return torch.as_tensor(holder, device="cuda:%d" % target.device)
+
+
+def make_window_allreduce(target, group=None):
+    """The ``magi_allreduce_fn`` callback (include/magi_b200.h) for ``run_hmc_sampler(window_allreduce=...)``: an in-place
+    sum over ranks of a device buffer, enqueued on the sampler's stream through ``torch.distributed`` (NCCL).  Returns a
+    ctypes function pointer; keep a reference to it for as long as the sampler may call it."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    dev = "cuda:%d" % target.device
+
+    def _cb(ptr, n, stream, user):
+        try:
+            class _Holder:
+                pass
+            holder = _Holder()
+            holder.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+            t = torch.as_tensor(holder, device=dev)
+            ext = torch.cuda.ExternalStream(int(stream) if stream else 0, device=dev) if stream else torch.cuda.default_stream(dev)
+            with torch.cuda.stream(ext):
+                if dist.is_initialized() and dist.get_world_size(group) > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception:                                   # nothing may propagate through the C frame
+            import traceback
+            traceback.print_exc()
+            return 1
+    return _lib.ALLREDUCE_FN(_cb)

@@ -15,9 +15,15 @@ from .target import MagiTarget
 
 def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n_adapts: int = 1000,
                     target_accept_ratio: float = 0.8, initial_step_size: float = 0.1, n_leapfrog: int = 20,
-                    seed: int = 0, chain_id_offset: int = 0, keep_on_device: bool = False):
+                    seed: int = 0, chain_id_offset: int = 0, keep_on_device: bool = False,
+                    n_chains_total: int | None = None, window_allreduce=None):
     """Argument meaning follows ``run_nuts_sampler``: ``n_samples`` is the TOTAL number of iterations including the
     ``n_adapts`` warm-up iterations, which are dropped (``drop_warmup=true``).  ``initial_params`` is (n_chains, P).
+
+    Multi-rank runs (chains sharded over GPUs): pass the global chain count as ``n_chains_total`` and
+    ``window_allreduce = distributed.make_window_allreduce(target)``; the pooled metric of the warm-up is then a statistic
+    of ALL ranks' chains, and the run is bit-identical to a one-rank run over the same global chains (shards aligned to
+    ``n_chains_total / 64`` chains).
 
     Returns ``(chain, stats)``: ``chain`` is an array (n_kept, n_chains, k + D + 1) of (θ, σ, lp) draws and ``stats`` a
     dict with per-chain acceptance rate, step size, divergences, posterior mean of X, the adapted inverse metric and
@@ -31,6 +37,10 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
     nc = p0.shape[0]
     h = target._h
     _lib.check(L.magi_hmc_init(h, nc, _lib.as_dp(p0), ctypes.c_ulonglong(seed), float(initial_step_size), ctypes.c_longlong(chain_id_offset)))
+    if n_chains_total is not None or window_allreduce is not None:
+        cb = window_allreduce if window_allreduce is not None else ctypes.cast(None, _lib.ALLREDUCE_FN)
+        target._window_allreduce = cb                      # keep the ctypes callback alive as long as the handle
+        _lib.check(L.magi_hmc_set_global(h, ctypes.c_longlong(int(n_chains_total if n_chains_total is not None else nc + chain_id_offset)), cb, None))
     if n_adapts > 0:
         _lib.check(L.magi_hmc_run(h, int(n_adapts), int(n_leapfrog), 1, float(target_accept_ratio), 0, None))
     _lib.check(L.magi_hmc_reset_stats(h))

@@ -103,6 +103,56 @@ def test_hmc_is_reproducible_bit_for_bit(pkg):
     assert np.array_equal(s1["step_size"], s2["step_size"]) and np.array_equal(s1["inverse_metric"], s2["inverse_metric"])
 
 
+def test_hmc_warmup_is_invariant_to_sharding(pkg):
+    """Two "ranks" (two handles driven by two threads on one GPU) with the window all-reduce callback reproduce a one-rank
+    run bit for bit, warm-up included: the pooled metric is reduced over fixed slices of GLOBAL chain ids in a fixed order
+    (magi_hmc_set_global, include/magi_b200.h).  The callback here sums the two ranks' buffers through the host."""
+    import threading
+    import torch
+    from manifold_constrained_gaussian_process_inference_b200 import _lib
+    prob = H.make_problem(n=41, T=8.0, b=6, n_chains=8, seed=13, obs_every=2)
+    rng = np.random.default_rng(5)
+    params = np.repeat(prob["params"], 16, axis=0) + 1e-3 * rng.normal(size=(128, prob["params"].shape[1]))
+    kw = dict(n_samples=60, n_adapts=45, initial_step_size=0.002, n_leapfrog=5, seed=9)
+    full, st_full = pkg.run_hmc_sampler(H.cuda_target(pkg, prob), params, n_chains_total=128, **kw)
+
+    barrier = threading.Barrier(2)
+    slots = [None, None]
+
+    def make_cb(rank):
+        def cb(ptr, n, stream, user):
+            class _Holder:
+                pass
+            hld = _Holder()
+            hld.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+            t = torch.as_tensor(hld, device="cuda:0")
+            torch.cuda.synchronize()
+            slots[rank] = t.cpu()
+            barrier.wait()
+            total = slots[0] + slots[1]
+            barrier.wait()
+            t.copy_(total.to("cuda:0"))
+            torch.cuda.synchronize()
+            return 0
+        return _lib.ALLREDUCE_FN(cb)
+
+    out = [None, None]
+
+    def worker(rank):
+        tg = H.cuda_target(pkg, prob)
+        chain, st = pkg.run_hmc_sampler(tg, params[64 * rank:64 * (rank + 1)], chain_id_offset=64 * rank, n_chains_total=128,
+                                        window_allreduce=make_cb(rank), **kw)
+        out[rank] = (chain, st)
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in threads: t.start()
+    for t in threads: t.join(timeout=120)
+    assert out[0] is not None and out[1] is not None
+    assert np.array_equal(full[:, :64], out[0][0]) and np.array_equal(full[:, 64:], out[1][0])
+    assert np.array_equal(st_full["inverse_metric"], out[0][1]["inverse_metric"])
+    assert np.array_equal(st_full["step_size"][:64], out[0][1]["step_size"]) and np.array_equal(st_full["step_size"][64:], out[1][1]["step_size"])
+
+
 def test_hmc_energy_conservation_and_reversibility_proxy(pkg):
     """With a tiny step the acceptance probability must be ~1 (the leapfrog integrates the gradient the kernel returns)."""
     prob = H.make_problem(n=41, T=8.0, b=6, n_chains=32, seed=2)

@@ -32,7 +32,8 @@ torch.cuda.synchronize()
 if world > 1: dist.barrier()
 t0 = time.perf_counter()
 chain, st = pkg.run_hmc_sampler(tg, params, n_samples=args.iters, n_adapts=args.warmup, initial_step_size=0.002, n_leapfrog=args.leapfrog,
-                                seed=20251018 + 5, chain_id_offset=first, keep_on_device=True)
+                                seed=20251018 + 5, chain_id_offset=first, keep_on_device=True, n_chains_total=args.chains,
+                                window_allreduce=D.make_window_allreduce(tg) if world > 1 else None)
 torch.cuda.synchronize()
 t_sample = time.perf_counter() - t0
 draws = D.device_draws_as_tensor(tg)
