@@ -202,6 +202,22 @@ def main():
         ms = float(t.item())
 
     # ---- e2e: the public host API (HOST buffers in, HOST buffers out; copies inside the timed region) ----
+    # The pinned buffers are allocated, and the calls are made, from the CPUs NVML reports as local to this GPU (what
+    # `numactl` would do): on a multi-socket box a process that lands on the far socket sees half the PCIe bandwidth.
+    old_affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (ncpu + 63) // 64)
+        cpus = {64 * wi + bit for wi, wd in enumerate(words) for bit in range(64) if (wd >> bit) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            old_affinity = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        old_affinity = None
     hp = torch.from_numpy(work["params"]).pin_memory()
     hg = torch.empty_like(hp).pin_memory()
     hl = torch.empty(chains, dtype=torch.float64).pin_memory()
@@ -226,6 +242,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     clocks = sampler.stop() if sampler else None
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)          # the CPU baseline below uses every host core
 
     if rank == 0:
         peaks = load_peaks()
