@@ -114,6 +114,30 @@ def test_large_batch_paths(pkg, model, n, b, nc, what):
     H.assert_parity(ll[sub], g[sub], ll2, g2, what + " (vs small batch)")
 
 
+@pytest.mark.parametrize("model,n,b,nc", [("fn", 201, 20, 37), ("fn", 41, 6, 2400), ("lv", 150, 40, 37), ("fn", 120, 119, 200)])
+def test_device_call_stays_inside_its_buffers(pkg, model, n, b, nc):
+    """The device-pointer entry (magi_logdensity_and_gradient_batched_dev) writes ll[0 : n_chains] and grad[0 : n_chains * P] and
+    nothing else: guard bands around both buffers keep their sentinel, for partial blocks (chain counts that are not a multiple
+    of 8 / 16 / 32), both block shapes and the GEMM path with its remainder strips."""
+    import torch
+    prob = H.make_problem(model=model, n=n, b=b, n_chains=8, seed=n + nc, T=0.06 * n)
+    rng = np.random.default_rng(nc)
+    params = np.repeat(prob["params"], (nc + 7) // 8, axis=0)[:nc] + 1e-3 * rng.normal(size=(nc, prob["params"].shape[1]))
+    tg = H.cuda_target(pkg, prob)
+    P, guard, sentinel = params.shape[1], 4096, -7.25
+    dev = torch.device("cuda")
+    p = torch.from_numpy(params).to(dev)
+    gbuf = torch.full((nc * P + 2 * guard,), sentinel, dtype=torch.float64, device=dev)
+    lbuf = torch.full((nc + 2 * guard,), sentinel, dtype=torch.float64, device=dev)
+    tg.logdensity_and_gradient_batched_dev(nc, p.data_ptr(), lbuf.data_ptr() + 8 * guard, gbuf.data_ptr() + 8 * guard, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    g, l = gbuf.cpu().numpy(), lbuf.cpu().numpy()
+    assert np.all(g[:guard] == sentinel) and np.all(g[-guard:] == sentinel) and np.all(l[:guard] == sentinel) and np.all(l[-guard:] == sentinel)
+    assert np.array_equal(p.cpu().numpy(), params)                      # the inputs are read-only
+    ll, grad = tg.logdensity_and_gradient_batched(params)
+    assert np.array_equal(l[guard:-guard], ll) and np.array_equal(g[guard:-guard].reshape(nc, P), grad)
+
+
 def test_guards_per_chain(pkg):
     """interface.jl:179-182, 222-226: wrong length -> (-Inf, NaN...); a non-finite chain -> (-Inf, 0...) without
     poisoning its neighbours."""
