@@ -95,6 +95,8 @@ def test_batched_parity_random(pkg, model, n, b, nc, kw):
     ("fn", 201, 20, 2368, "K1 with two chain-groups per block, last batch size before the switch"),
     ("fn", 201, 20, 2369, "K1 with four chain-groups per block, partial last block"),
     ("fn", 201, 20, 5000, "K1 pipelined host call: chunks of different block shapes"),
+    ("lv", 1281, 20, 2400, "BASELINE config 3 time axis: Ke scratch in L2, four chain-groups per block"),
+    ("lv", 1281, 20, 300, "BASELINE config 3 time axis: Ke scratch in L2, two chain-groups per block"),
 ])
 def test_large_batch_paths(pkg, model, n, b, nc, what):
     """Code paths that only large batches reach (persistent stream-K GEMM of the dense mode; the per-call block shape of the
