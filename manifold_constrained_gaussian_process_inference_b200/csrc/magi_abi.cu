@@ -38,6 +38,7 @@ extern "C" int magi_destroy(magi_handle* h) {
     free_dev(h->d_fragtab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
     free_dev(h->d_dense_work); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
+    free_dev(h->d_small); if (h->h_pin) cudaFreeHost(h->h_pin);
     hmc_free(h);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 3; ++i) if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);
@@ -275,6 +276,29 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
             if (grad) CK(cudaMemcpyAsync(grad + off, h->d_grad + off, sizeof(double) * (size_t)nc * h->P, cudaMemcpyDeviceToHost, st), "D2H grad");
         }
         for (int k = 0; k < 3; ++k) CK(cudaStreamSynchronize(h->pipe_streams[k]), "stream sync");
+        return MAGI_OK;
+    }
+    // Small calls (the single-chain drop-in of the reference's NUTS loop): pinned staging on both sides and ONE device-to-host
+    // copy of a contiguous [ll | grad] block instead of two copies into pageable memory.
+    const size_t np_d = (size_t)n_chains * h->P, nl_pad = ((size_t)n_chains + 7) / 8 * 8;
+    if (np_d + nl_pad <= (size_t)65536) {
+        const size_t half = 65536 + 8;
+        if (!h->h_pin) {
+            CK(cudaMallocHost(&h->h_pin, sizeof(double) * 2 * half), "cudaMallocHost staging");
+            CK(cudaMalloc(&h->d_small, sizeof(double) * 2 * half), "cudaMalloc small-call staging");
+            h->small_cap = half;
+        }
+        double* d_in = h->d_small;
+        double* d_out = h->d_small + half;               // [ll (padded to 8) | grad]
+        memcpy(h->h_pin, params, nb);
+        CK(cudaMemcpyAsync(d_in, h->h_pin, nb, cudaMemcpyHostToDevice, h->stream), "H2D params");
+        rc = eval_dev(h, n_chains, d_in, h->P, d_out, grad ? d_out + nl_pad : nullptr, h->stream);
+        if (rc) return rc;
+        const size_t out_d = grad ? nl_pad + np_d : (size_t)n_chains;
+        CK(cudaMemcpyAsync(h->h_pin + half, d_out, sizeof(double) * out_d, cudaMemcpyDeviceToHost, h->stream), "D2H ll | grad");
+        CK(cudaStreamSynchronize(h->stream), "stream sync");
+        memcpy(ll, h->h_pin + half, sizeof(double) * n_chains);
+        if (grad) memcpy(grad, h->h_pin + half + nl_pad, nb);
         return MAGI_OK;
     }
     CK(cudaMemcpyAsync(h->d_params, params, nb, cudaMemcpyHostToDevice, h->stream), "H2D params");

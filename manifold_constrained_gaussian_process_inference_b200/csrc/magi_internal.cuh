@@ -23,6 +23,9 @@ struct magi_handle {
     // host-API staging
     double *d_params = nullptr, *d_ll = nullptr, *d_grad = nullptr;
     size_t cap_chains = 0;
+    // small host-buffer calls (the single-chain drop-in): pinned staging and one contiguous [ll | grad] output block
+    double *h_pin = nullptr, *d_small = nullptr;
+    size_t small_cap = 0;                 // doubles per staging half
     double* d_scratch = nullptr;
     size_t scratch_cap = 0;
     // dense-mode work space
