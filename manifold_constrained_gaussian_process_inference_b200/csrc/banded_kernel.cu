@@ -4,20 +4,8 @@
 //   log_likelihood_and_gradient_banded          src/likelihoods.jl:43-257
 //   LogDensityProblems.logdensity_and_gradient  src/logdensityproblems_interface.jl:176-267
 //
-// Formulation.  For every dimension d the four band products (m~ x, K~ e, C~ x, m~^T Ke; likelihoods.jl:129,132,133,192)
-// are written as (chains x time) = (chains x time) . (band table) products: 8 chains form the M extent of a
-// DMMA.8x8x4, 8 output times its N extent, and the contraction runs over 4-time chunks.  A warp owns one
-// (chain-group, dimension) task and sweeps the time axis once per phase; the operand (x, e, Ke) lives in a register
-// window of WN chunks that slides by one 8-time tile per step, so every state value is read from memory once per
-// sweep and the only per-DMMA load is the 256-byte table fragment (shared by every chain on the GPU: L1/L2 hits).
-// The time->slot permutation (lane (gid,q) owns times 8J+q and 8J+q+4 of tile J) makes the C fragment of one
-// product directly usable as the A fragment of the next, so x -> e -> Ke never leaves registers.
-//
-//   phase A1 (per task):  mx = m~ x_d;  e = f_d(x, theta) - mx;  Ke = K~ e  -> Ke to scratch; sum e.Ke
-//   phase A2 (per task):  Cx = C~ x_d;  mt = m~^T Ke_d;  pointwise gradient incl. the ODE Jacobian terms, which need
-//                         Ke of ALL dimensions at the same time point (hence the block-wide barrier in between)
-//   final   (per chain):  log-likelihood assembly in the reference's term order, sigma gradient, log-sigma
-//                         transform and the per-chain -Inf / zero-gradient guards.
+// The kernel, its formulation (8 chains x 8 output times per DMMA, contraction over 4-time chunks, sliding register windows,
+// warp roles, queues and fragment rings) are described in banded_kernel.cuh and DESIGN.md section 4.
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -97,11 +85,12 @@ bool model_dims(int model, int& D, int& K) {
 
 size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)G * D * NT * 64; }   // Ke
 
-// Chooses chain-groups per block (G), time segments (H), concurrently processed dimensions (DW) and where the Ke scratch
-// lives.  Preference: 16 warps per block (one block per SM, <= 128 registers), as many chain-groups as possible sharing a
-// fragment ring, two time segments when the time axis is long enough to amortise the halo.
+// Chooses chain-groups per block (G <= gmax, a power of two) and where the Ke scratch lives (H and DW are fixed: one time
+// segment, all dimensions concurrently).  Preference: 16 warps per block (one block per SM, <= 128 registers), as many
+// chain-groups as possible sharing the fragment rings.
 void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, int& G, int& H, int& DW, int& scratch_in_smem, size_t& smem_bytes) {
-    const int RED = 4 + K, NCH = 2 * HB + 2;
+    const int NCH = 2 * HB + 2;
+    (void)K;
     DW = D;
     H = 1;
     if (gmax < 1 || gmax > 4) gmax = 4;
@@ -118,9 +107,8 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, 
         if (2 * g * D > 16 || (g & (g - 1)) != 0) continue;      // powers of two only (the ring producer rotates with r & (G - 1))
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0 && force_global) continue;
-            size_t red = 0;   // aliased
             size_t scr = pass == 0 ? banded_scratch_doubles_per_cta(g, D, NT) * sizeof(double) : 0;
-            size_t tot = scr + fixed_bytes(g) + red;
+            size_t tot = scr + fixed_bytes(g);      // (the per-chain reduction area aliases the queues)
             if (tot <= (size_t)smem_limit) { G = g; scratch_in_smem = (pass == 0); smem_bytes = tot; return; }
         }
     }
