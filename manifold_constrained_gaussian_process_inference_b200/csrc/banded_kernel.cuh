@@ -71,8 +71,6 @@ __device__ __forceinline__ void mbar_wait2(unsigned long long* bar_a, unsigned p
     }
     __trap();
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
