@@ -42,6 +42,9 @@ def _compile(src, extra):
 
 
 def build(force: bool = False, fast: bool = False, verbose: bool = False) -> str:
+    global OBJDIR
+    if fast and "MAGI_OBJ_DIR" not in os.environ:
+        OBJDIR = os.path.join(HERE, "build_fast")      # objects compiled with -DMAGI_FAST_BUILD must never be linked into a full build
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     extra = {"force": force, "defs": (["-DMAGI_FAST_BUILD"] if fast else []) + os.environ.get("MAGI_EXTRA_DEFS", "").split()}

@@ -15,8 +15,7 @@
 namespace magi {
 
 // ------------------------------------------------------------------------------------------------------------
-// K6: fragment tables.  fragtab[view][d][pair p][hh][lane][tt]: pair p holds the tiles J = 2p - off + tt, tt = 0, 1
-// (off = LAGT & 1 for the views m~, C~, m~^T, whose sweep runs LAGT tiles behind the window head; 0 for K~), interleaved per
+// K6: fragment tables.  fragtab[view][d][pair p][hh][lane][tt]: pair p holds the tiles J = 2p + tt, tt = 0, 1, interleaved per
 // lane so that one 16-byte load fetches chunk hh of BOTH tiles -- the two DMMAs it feeds belong to different accumulate
 // chains.  lane = 4*gid + q holds the B-operand entry
 //   T[in = 4*(2J - HB + hh) + q][out = 8J + (gid>>1) + 4*(gid&1)]
@@ -25,13 +24,13 @@ namespace magi {
 // ------------------------------------------------------------------------------------------------------------
 size_t fragtab_doubles(int n, int b, int D) {
     BandGeom g = band_geom(n, b);
-    return (size_t)4 * D * (g.NT / 2 + 1) * g.NCH * 64;
+    return (size_t)4 * D * ((g.NT + 1) / 2) * g.NCH * 64;
 }
 
 __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const double* __restrict__ band_mphi,
                                      const double* __restrict__ band_kinv, double* __restrict__ fragtab,
-                                     int n, int b, int D, int HB, int NCH, int NT, int LAGT) {
-    const int NP = NT / 2 + 1;
+                                     int n, int b, int D, int HB, int NCH, int NT) {
+    const int NP = (NT + 1) / 2;
     const size_t per_view = (size_t)D * NP * NCH * 64;
     const size_t total = 4 * per_view;
     const size_t tab = (size_t)(2 * b + 1) * n;
@@ -42,7 +41,7 @@ __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const
         int p = (int)(r % NP); r /= NP;
         int d = (int)(r % D);
         int view = (int)(r / D);
-        const int J = 2 * p - (view == 2 ? 0 : (LAGT & 1)) + tt;
+        const int J = 2 * p + tt;
         int gid = lane >> 2, q = lane & 3;
         int o = 8 * J + (gid >> 1) + 4 * (gid & 1);
         int i = 4 * (2 * J - HB + hh) + q;
@@ -62,7 +61,7 @@ cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mph
     size_t total = fragtab_doubles(n, b, D);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT, g.LAGT);
+    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT);
     return cudaGetLastError();
 }
 

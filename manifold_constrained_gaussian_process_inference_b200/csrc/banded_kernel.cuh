@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     constexpr int NCH = 2 * HB + 2, LAGT = (HB + 1) / 2, W2 = 2 * LAGT + 4 + HB;
     constexpr int RED = 4 + K;   // e.Ke, x.Cx, sse, bad flag, theta-gradient partials
     constexpr int BLKP = NCH * 64;              // doubles per fragment pair-block (one view, two tiles interleaved per lane)
-    constexpr int OFF = LAGT & 1, LAGP = LAGT >> 1;   // pair p of views m~, C~, m~^T holds tiles (2p - OFF, 2p - OFF + 1); of K~ (2p, 2p + 1)
+    // Every view is stored in pairs of tiles (2p, 2p + 1).  The products with m~, C~, m~^T run LAGT tiles behind the window head;
+    // when LAGT is odd the window heads are the tile pairs (2u - 1, 2u) (HO = 1), so that the OUTPUT pairs are (2p, 2p + 1) as
+    // well and no output pair straddles an end of the time axis; the e window is 2 HO chunks longer so that the K~ output pairs
+    // (LAGT + HO tiles behind the e pairs) are aligned the same way.
+    constexpr int HO = LAGT & 1, LAGH = (LAGT + HO) / 2, W2E = W2 + 2 * HO;
     constexpr int S = kXStages, R = kRingStages, XS = kXSlots;
     extern __shared__ __align__(128) double smem[];
     const int NT = a.NT, n = a.n, G = a.G;
@@ -168,10 +172,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         v0 = (t0 >= 0 && t0 < n) ? base[t0] : 0.0;
         v1 = (t1 >= 0 && t1 < n) ? base[t1] : 0.0;
     };
-    const int NP = NT / 2 + 1;                      // pair-blocks per (view, dimension)
-    const int NPK = (NT + 1) / 2;                   // K~ pairs that hold a tile of the time axis (pairs (2p, 2p+1): no offset)
-    constexpr int LE = LAGP + OFF;                  // the K~ pair pb is computed right after e pair pb + LE has entered the window
-    const int N2 = (NT - 1 + LAGT) / 2 + 1;         // A2 steps: the output pair (2u - LAGT, +1) reaches tile NT - 1
+    const int NP = (NT + 1) / 2;                    // pair-blocks per (view, dimension): tiles (2p, 2p + 1)
     auto pair_ok = [&](int pp) { return pp >= 0 && pp < NP; };
     // One elected thread streams pair-block `src` (null: nothing to load, the barrier still completes) into stage r mod R of
     // a ring, after every consumer warp has released use r - R.  The producer duty rotates over the G consumer warps of the
@@ -197,27 +198,27 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         const double* ft1 = a.fragtab + ((size_t)(1 * D + d) * NP) * BLKP;   // C~
         const double* ft2 = a.fragtab + ((size_t)(2 * D + d) * NP) * BLKP;   // K~
         const double* ft3 = a.fragtab + ((size_t)(3 * D + d) * NP) * BLKP;   // m~^T
-        // ring B use r: A1 K~ pair r (r < NPK); A2 step u = r - NPK: C~ pair into ring A's buffer and m~^T pair into ring B's,
+        // ring B use r: A1 K~ pair r (r < NP); A2 step u = r - NP: C~ pair into ring A's buffer and m~^T pair into ring B's,
         // both signalled on ring B's barriers (the pointwise warps no longer use ring A then)
         auto issue_b = [&](int r) {
-            if (r < NPK) ring_issue(r, ringB, bfull, bempty, ft2 + (size_t)r * BLKP, nullptr, nullptr);
-            else if (r < NPK + N2) {
-                const int pc = r - NPK - LAGP;
+            if (r < NP) ring_issue(r, ringB, bfull, bempty, ft2 + (size_t)r * BLKP, nullptr, nullptr);
+            else if (r < 2 * NP) {
+                const int pc = r - NP;
                 ring_issue(r, ringB, bfull, bempty, pair_ok(pc) ? ft3 + (size_t)pc * BLKP : nullptr, ringA, pair_ok(pc) ? ft1 + (size_t)pc * BLKP : nullptr);
             }
         };
         issue_b(0);
-        if (NPK > 1) issue_b(1);
+        if (NP > 1) issue_b(1);
         double acc_eke = 0.0, acc_xcx = 0.0;
         // ---------------- A1: Ke = K~ e (likelihoods.jl:132); e tiles come from the pointwise warp ----------------
         {
-            double ew[W2];
+            double ew[W2E];
 #pragma unroll
-            for (int i = 0; i < W2; ++i) ew[i] = 0.0;
+            for (int i = 0; i < W2E; ++i) ew[i] = 0.0;
             double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
             auto a1_step = [&](int i, auto in_, auto vb_) {
                 constexpr bool IN = decltype(in_)::value, VB = decltype(vb_)::value;   // IN: an e pair arrives; VB: a K~ pair is computed
-                const int pb = i - LE, st = pb % R, qs = i % S;
+                const int pb = i - LAGH, st = pb % R, qs = i % S;
                 double e4[4] = {0.0, 0.0, 0.0, 0.0};
 #ifdef MAGI_DBG_WAITS
                 long long w0 = clock64();
@@ -233,9 +234,9 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     e4[0] = xs[0]; e4[1] = xs[32]; e4[2] = xs[64]; e4[3] = xs[96];
                 }
 #pragma unroll
-                for (int j = 0; j < W2 - 4; ++j) ew[j] = ew[j + 4];
+                for (int j = 0; j < W2E - 4; ++j) ew[j] = ew[j + 4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ew[W2 - 4 + j] = e4[j];
+                for (int j = 0; j < 4; ++j) ew[W2E - 4 + j] = e4[j];
                 if constexpr (VB) {
                     const double2* fr = reinterpret_cast<const double2*>(ringB + (size_t)st * BLKP) + lane;
                     double k[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     }
                     __syncwarp();
                     if (lane == 0) { if (IN) mbar_arrive(q1empty + qs); mbar_arrive(bempty + st); }
-                    if (pb + 2 < NPK) issue_b(pb + 2);         // (the A2 uses wait for the block barrier: the pointwise warps may still read ring A)
+                    if (pb + 2 < NP) issue_b(pb + 2);         // (the A2 uses wait for the block barrier: the pointwise warps may still read ring A)
 #pragma unroll
                     for (int tt = 0; tt < 2; ++tt) {
                         if (tile_ok(2 * pb + tt)) {
@@ -262,9 +263,9 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     if (lane == 0) mbar_arrive(q1empty + qs);
                 }
             };
-            // e pairs arrive for i in [0, NP), K~ pairs are computed for i in [LE, NPK + LE): one loop per combination
-            const int iend = max(NP, NPK + LE);
-            int bp[4] = {0, min(LE, iend), min(NP, iend), min(NPK + LE, iend)};
+            // e pairs arrive for i in [0, NP), K~ pairs are computed for i in [LAGH, NP + LAGH): one loop per combination
+            const int iend = NP + LAGH;
+            int bp[4] = {0, min(LAGH, iend), min(NP, iend), min(NP + LAGH, iend)};
             if (bp[1] > bp[2]) { const int t = bp[1]; bp[1] = bp[2]; bp[2] = t; }
             if (bp[2] > bp[3]) { const int t = bp[2]; bp[2] = bp[3]; bp[3] = t; }
             if (bp[1] > bp[2]) { const int t = bp[1]; bp[1] = bp[2]; bp[2] = t; }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             for (int seg = 0; seg < 4; ++seg) {
                 const int i0 = bp[seg], i1 = seg < 3 ? bp[seg + 1] : iend;
                 if (i0 >= i1) continue;
-                const bool in = i0 < NP, vb = (i0 >= LE) && (i0 < NPK + LE);
+                const bool in = i0 < NP, vb = (i0 >= LAGH) && (i0 < NP + LAGH);
                 if (in && vb) {
 #pragma unroll 1
                     for (int i = i0; i < i1; ++i) a1_step(i, std::true_type{}, std::true_type{});
@@ -299,31 +300,35 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             for (int i = 0; i < W2; ++i) { xw[i] = 0.0; kw[i] = 0.0; }
             const double* ks = kscr + ((size_t)(g * D + d) * NT) * 64 + lane;
             auto load_feed = [&](int u, double (&fx)[4], double (&fk)[4]) {
-                ld2(xd, 2 * u, fx[0], fx[1]); ld2(xd, 2 * u + 1, fx[2], fx[3]);
+                ld2(xd, 2 * u - HO, fx[0], fx[1]); ld2(xd, 2 * u - HO + 1, fx[2], fx[3]);      // window heads of step u
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt) {
-                    const bool ok = tile_ok(2 * u + tt);
-                    fk[2 * tt] = ok ? ks[(size_t)(2 * u + tt) * 64] : 0.0;
-                    fk[2 * tt + 1] = ok ? ks[(size_t)(2 * u + tt) * 64 + 32] : 0.0;
+                    const int J = 2 * u - HO + tt;
+                    const bool ok = tile_ok(J);
+                    fk[2 * tt] = ok ? ks[(size_t)(ok ? J : 0) * 64] : 0.0;
+                    fk[2 * tt + 1] = ok ? ks[(size_t)(ok ? J : 0) * 64 + 32] : 0.0;
                 }
             };
-            load_feed(0, nf, nk);
+            // the windows start out filled up to the heads of step LAGH (the first step with an output pair): no lead-in steps
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
-            const int uc0 = min(LAGP, N2), uc1 = min(NP + LAGP, N2);
+            for (int k = 0; k <= LAGH; ++k) {
+                load_feed(LAGH - k, nf, nk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (W2 - 4 - 4 * k + i >= 0) { xw[W2 - 4 - 4 * k + i] = nf[i]; kw[W2 - 4 - 4 * k + i] = nk[i]; }
+            }
             // ping-pong partner: the other DMMA warp on this SM sub-partition (warp ^ 4), named barriers 1..8
             const bool pp_partner = ((warp ^ 4) < ntask) && a.H == 0, pp_first = warp < 4;
             const int pp_mine = 1 + 2 * (warp & 3) + (pp_first ? 0 : 1), pp_other = 1 + 2 * (warp & 3) + (pp_first ? 1 : 0);
-            auto a2_step = [&](int u, auto v_) {
-                constexpr bool V = decltype(v_)::value;
-                const int r = NPK + u;
-                const int st = r % R, qs = u % S;
+            auto a2_step = [&](int pc) {                     // output pair pc = tiles (2 pc, 2 pc + 1); window heads of step u = pc + LAGH
+                const int u = pc + LAGH, r = NP + pc;
+                const int st = r % R, qs = pc % S;
                 double* xs = xq + (size_t)qs * XS * 32;
 #ifdef MAGI_DBG_WAITS
                 long long w0 = clock64();
 #endif
                 // fragments of this step; the pointwise warp has read the tiles of step u - S
-                if (u >= S) mbar_wait2(bfull + st, (r / R) & 1, q2empty + qs, ((u / S) - 1) & 1);
+                if (pc >= S) mbar_wait2(bfull + st, (r / R) & 1, q2empty + qs, ((pc / S) - 1) & 1);
                 else mbar_wait(bfull + st, (r / R) & 1);
 #ifdef MAGI_DBG_WAITS
                 wfull += clock64() - w0;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 const double2* fra = reinterpret_cast<const double2*>(ringA + (size_t)st * BLKP) + lane;
                 const double2* frb = reinterpret_cast<const double2*>(ringB + (size_t)st * BLKP) + lane;
                 double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, um[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                if constexpr (V) {
+                {
                     // The two DMMA warps of an SM sub-partition take turns on the FP64 tensor pipe: while one issues its 48 DMMAs
                     // (16 clk each, alone on the pipe) the other does its non-DMMA part of the step.  Left alone they run in
                     // lock-step (same ring barrier releases both), share the pipe during the DMMA blocks and leave it idle
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                         dmma884(c[0][0], c[0][1], xw[hh], fa.x);    dmma884(c[1][0], c[1][1], xw[hh + 2], fa.y);     // likelihoods.jl:133
                         dmma884(um[0][0], um[0][1], kw[hh], fb.x);  dmma884(um[1][0], um[1][1], kw[hh + 2], fb.y);   // likelihoods.jl:192
                     }
-                    if (pp_partner && (pp_first || u + 1 < uc1)) named_arrive(pp_other, 64);
+                    if (pp_partner && (pp_first || pc + 1 < NP)) named_arrive(pp_other, 64);
                 }
                 // the DMMA warp has slack in this phase: it combines the two products (likelihoods.jl:186,194) and accumulates
                 // x.Cx (:150; x and Cx are both zero outside the time axis), the pointwise warp gets one value per point
@@ -363,15 +368,10 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { xw[W2 - 4 + i] = nf[i]; kw[W2 - 4 + i] = nk[i]; }
             };
-            issue_b(NPK); issue_b(NPK + 1);                      // (after the block barrier: ring A's buffer is free now)
-            if (pp_partner && !pp_first && uc1 > uc0) named_arrive(pp_other, 64);      // the first warp of the pair may start
-            int u = 0;
+            issue_b(NP); issue_b(NP + 1);                      // (after the block barrier: ring A's buffer is free now)
+            if (pp_partner && !pp_first && NP > 0) named_arrive(pp_other, 64);      // the first warp of the pair may start
 #pragma unroll 1
-            for (; u < uc0; ++u) a2_step(u, std::false_type{});
-#pragma unroll 1
-            for (; u < uc1; ++u) a2_step(u, std::true_type{});
-#pragma unroll 1
-            for (; u < N2; ++u) a2_step(u, std::false_type{});
+            for (int pc = 0; pc < NP; ++pc) a2_step(pc);
         }
         if (a.dbg) tk3 = clock64();
         __syncthreads();                                     // the queues are dead: `red` may overwrite them
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
         M::prepare(th);
         // ---------------- A1: mx = m~ x_d (likelihoods.jl:129), e = f(x, theta) - mx (:130) -> queue, ahead of the DMMA warp ----------------
-        // step u: output tiles (Ja, Ja+1) = (2u - LAGT, +1) = m~ pair pa = u - LAGP; the x window head is at tiles (2u, 2u+1)
+        // step pa: output tiles (Ja, Ja+1) = m~ pair pa (Ja = 2 pa); the x window head is at tiles (2u - HO, 2u - HO + 1), u = pa + LAGH
         {
             const double* xd = xp + (size_t)d * n;
             const double* ft0 = a.fragtab + ((size_t)(0 * D + d) * NP) * BLKP;   // m~
@@ -396,10 +396,18 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
             double xw[W2], nf[4];
 #pragma unroll
             for (int i = 0; i < W2; ++i) xw[i] = 0.0;
-            ld2(xd, 0, xw[W2 - 4], xw[W2 - 3]); ld2(xd, 1, xw[W2 - 2], xw[W2 - 1]);   // window head of step 0: tiles 0, 1
-            auto a1_step = [&](int u, auto va_) {
-                constexpr bool VA = decltype(va_)::value;
-                const int Ja = 2 * u - LAGT, pa = u - LAGP, st = pa % R, qs = pa % S;
+            // the window starts out filled up to the heads of step LAGH (the first step with an output pair): no lead-in steps
+#pragma unroll
+            for (int k = 0; k <= LAGH; ++k) {
+                double h4[4];
+                ld2(xd, 2 * (LAGH - k) - HO, h4[0], h4[1]); ld2(xd, 2 * (LAGH - k) - HO + 1, h4[2], h4[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (W2 - 4 - 4 * k + i >= 0) xw[W2 - 4 - 4 * k + i] = h4[i];
+            }
+            auto a1_step = [&](int pa) {
+                constexpr bool VA = true;
+                const int u = pa + LAGH, Ja = 2 * pa, st = pa % R, qs = pa % S;
                 if constexpr (VA) {
 #ifdef MAGI_DBG_WAITS
                     long long w0 = clock64();
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     wq += clock64() - w0;
 #endif
                 }
-                ld2(xd, 2 * u + 2, nf[0], nf[1]); ld2(xd, 2 * u + 3, nf[2], nf[3]);    // window feed of step u+1 (entered at the end)
+                ld2(xd, 2 * u + 2 - HO, nf[0], nf[1]); ld2(xd, 2 * u + 3 - HO, nf[2], nf[3]);    // window feed of step u+1 (entered at the end)
                 double xo[2][2][D];                  // the other components at the output points (this one is in the window)
 #pragma unroll
                 for (int tt = 0; tt < 2; ++tt)
@@ -446,11 +454,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                 for (int j = 0; j < 4; ++j) xw[W2 - 4 + j] = nf[j];
             };
-            int u = 0;
 #pragma unroll 1
-            for (; u < LAGP; ++u) a1_step(u, std::false_type{});
-#pragma unroll 1
-            for (; u < NP + LAGP; ++u) a1_step(u, std::true_type{});
+            for (int pa = 0; pa < NP; ++pa) a1_step(pa);
         }
         // A2 prologue that does not depend on the Ke scratch
         double acc_sse = 0.0;
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         double nxa[2][2][D], nyv[2][2];
         // INTERIOR steps (both output tiles inside the time axis, all 16 times < n) run without bounds predicates and selects
         auto load_a2_int = [&](int u, double (&X)[2][2][D], double (&Y)[2][2]) {
-            const int Jc = 2 * u - LAGT;
+            const int Jc = 2 * u;
             const double* px = xp + 8 * Jc + q;
             const double* py = yd + 8 * Jc + q;
 #pragma unroll
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 }
         };
         auto load_a2 = [&](int u, double (&X)[2][2][D], double (&Y)[2][2]) {
-            const int Jc = 2 * u - LAGT;
+            const int Jc = 2 * u;
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
                 const int J = tile_ok(Jc + tt) ? Jc + tt : -4;
@@ -493,13 +498,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 ld2(yd, J, Y[tt][0], Y[tt][1]);
             }
         };
-        auto interior = [&](int u) { const int Jc = 2 * u - LAGT; return u < N2 && Jc >= 0 && 8 * (Jc + 1) + 7 < n; };
+        auto interior = [&](int u) { const int Jc = 2 * u; return u < NP && Jc >= 0 && 8 * (Jc + 1) + 7 < n; };
         load_a2(0, nxa, nyv);
         __syncthreads();
-        // ---------------- A2: pointwise gradient ----------------
+        // ---------------- A2: pointwise gradient; step u handles the output pair u = tiles (2u, 2u + 1) ----------------
         auto a2_step = [&](int u, auto int_) {
             constexpr bool INTERIOR = decltype(int_)::value;     // this step AND the next one are interior
-            const int Jc = 2 * u - LAGT, qs = u % S;
+            const int Jc = 2 * u, qs = u % S;
             double xa[2][2][D], wv[2][2][D], yv[2][2];
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt)
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                     yv[tt][pt] = nyv[tt][pt];
                 }
             if constexpr (INTERIOR) load_a2_int(u + 1, nxa, nyv);
-            else if (u + 1 < N2) load_a2(u + 1, nxa, nyv);
+            else if (u + 1 < NP) load_a2(u + 1, nxa, nyv);
             if constexpr (INTERIOR) {
                 const double* wsrc = kscr + ((size_t)(g * D) * NT + Jc) * 64 + lane;
 #pragma unroll
@@ -567,11 +572,11 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         {
             int u = 0;
 #pragma unroll 1
-            for (; u < N2 && !(interior(u) && interior(u + 1)); ++u) a2_step(u, std::false_type{});
+            for (; u < NP && !(interior(u) && interior(u + 1)); ++u) a2_step(u, std::false_type{});
 #pragma unroll 1
-            for (; u < N2 && interior(u) && interior(u + 1); ++u) a2_step(u, std::true_type{});
+            for (; u < NP && interior(u) && interior(u + 1); ++u) a2_step(u, std::true_type{});
 #pragma unroll 1
-            for (; u < N2; ++u) a2_step(u, std::false_type{});
+            for (; u < NP; ++u) a2_step(u, std::false_type{});
         }
         acc_sse = quad_sum(acc_sse);
 #pragma unroll

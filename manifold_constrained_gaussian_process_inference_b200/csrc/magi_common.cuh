@@ -42,7 +42,7 @@ struct BandedArgs {
     const double* params;
     double* ll;
     double* grad;               // may be null (value only)
-    const double* fragtab;      // [4 views][D][NT/2+1 pairs][NCH][32 lanes][2 tiles]
+    const double* fragtab;      // [4 views][D][(NT+1)/2 pairs][NCH][32 lanes][2 tiles]
     const double* yobs;         // [D][n], non-finite = missing
     const int* nobs;            // [D]
     const double* sigma_init;   // [D]
