@@ -89,9 +89,10 @@ template <int D, class F> __device__ __forceinline__ void dispatch_dim(int d, F&
     if constexpr (D >= 5) { if (d == 4) { f(std::integral_constant<int, 4>{}); return; } }
 }
 
-// Warp-specialised K1 (v12).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
+// Warp-specialised K1 (v13).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
 // warp ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers, one block per SM.  Operand windows (x, e, Ke)
-// live in registers and slide two 8-time tiles per step.  All hand-offs are ONE-DIRECTIONAL queues of kXStages stages in
+// live in registers, are prefilled in a prologue (every step of a sweep produces an output pair) and slide two 8-time tiles
+// per step.  All hand-offs are ONE-DIRECTIONAL queues of kXStages stages in
 // shared memory (a "full" and an "empty" mbarrier per stage), so neither warp waits for a round trip through the other:
 //   A1  P(u): mx = m~ x (x window), e = f(x, theta) - mx at tiles (Ja, Ja+1) -> queue (P runs ahead)
 //       C(i): e window <- queue; Ke pair = K~ e -> Ke scratch, sum e.Ke            (four DMMA-issuing warps per sub-partition)
