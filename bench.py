@@ -6,6 +6,11 @@
 
 One "step" = one logdensity_and_gradient pass over one batch of chains (BASELINE configs[1]: FitzHugh-Nagumo,
 n=201, band 20, 4096 chains per GPU).  Chains shard across ranks with no data-path collective (weak scaling).
+The timed block of --steps launches is repeated --repeats times (median reported, min / max beside it): a single block of
+20 launches is under a millisecond.  The own arm also measures, as extra keys of the same JSON line, BASELINE configs 3
+(`dense`: Lotka-Volterra n=1281, band n-1, 2048 chains), 4 (`setup`: Lorenz-96 D=64 n=2001 device GP setup, both modes)
+and 5 (`cfg5`: FN 65 536 chains split over the ranks, on-device HMC, one all-gather of the draws, R-hat / ESS);
+--sections none skips them.
 """
 from __future__ import annotations
 
@@ -108,6 +113,144 @@ def cpu_arm(work, tables, steps, warmup, chains, nthreads=0, min_seconds=0.0):
     return dict(evals_per_s=chains * done / dt, seconds=dt, passes=done, cores=(nthreads or c_oracle.num_threads()), ll=ll, grad=g)
 
 
+def host_cores():
+    """Every core this process may run on: torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+
+
+def section_dense(pkg, synthetic, torch, dev, local, peaks, reps=10):
+    """BASELINE config 3, dense mode: Lotka-Volterra n=1281, band n-1 (the FP64 DMMA GEMM path), 2048 chains, one GPU."""
+    w = synthetic.make_workload("lv1281", 2048)
+    n, D, nch = w["n"], w["D"], 2048
+    tg = pkg.MagiTarget.from_config(w["yobs"], w["tvec"], w["phi"], pkg.lv_system(), w["sigma_init"], bandsize=n - 1, jitter=1e-6,
+                                    setup_mode="stable", device=local, max_chains=nch)
+    p = torch.from_numpy(w["params"]).to(dev); g = torch.empty_like(p); ll = torch.empty(nch, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = tg.launch_count()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()                                       # 256 MB written: nothing of the previous pass is left in the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st); e1.record()
+        torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    launches = (tg.launch_count() - l0) // reps
+    clocks = sampler.stop()
+    ms = _median(ts)
+    flops = synthetic.algorithmic_flops_per_eval(n, D, n - 1)
+    tf = nch * flops / (ms * 1e-3) * 1e-12
+    finite = bool(torch.isfinite(ll).all().item())
+    tg.close()
+    return {"config": {"workload": "lv1281 dense: lv n=%d D=%d band=%d (= n-1) matern52 jitter=1e-6, %d chains, one GPU" % (n, D, n - 1, nch)},
+            "metric": "leapfrog grad evals/sec (all chains)", "value": nch / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms,
+            "ms_min": min(ts), "ms_max": max(ts), "repeats": reps, "gpu_launches": int(launches), "ll_finite": finite, "clocks": clocks,
+            "l2": "256 MB flush buffer written between timed passes",
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_tflops"],
+                         "kernel": "gemm_f64_dmma_streamk_kernel (4 GEMMs per evaluation) + 2 pointwise kernels",
+                         "algorithmic_flops_per_eval": flops, "peak_source": peaks["fp64_src"]}}
+
+
+def section_setup(pkg, torch, local, peaks):
+    """BASELINE config 4: Lorenz-96 D=64, n=2001: device GP setup (covariance build, blocked Cholesky, inverses, GEMMs, bands)."""
+    rng = np.random.default_rng(20251018 + 3)
+    n, D = 2001, 64
+    tvec = np.linspace(0.0, 20.0, n)
+    phi = np.stack([rng.uniform(10, 20, D), rng.uniform(0.2, 0.4, D)])
+    Y = np.full((n, D), np.nan); Y[::10] = 8.0 + rng.normal(size=(len(tvec[::10]), D))
+    out = {"config": {"workload": "lorenz96 setup: D=%d n=%d band=20 matern52 jitter=1e-6, 64 distinct (variance, lengthscale) pairs, one GPU" % (D, n)},
+           "modes": {}}
+    sampler = ClockSampler(local); sampler.start()
+    for mode in ("stable", "reference_order"):
+        best = None
+        for rep in range(2):                                # the first create of a process also pays the allocator's first 20 GB
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            tg = pkg.MagiTarget.from_config(Y, tvec, phi, pkg.get_ode_system("lorenz96", D), np.full(D, 0.5), bandsize=20, jitter=1e-6,
+                                            setup_mode=mode, device=local)
+            wall = time.perf_counter() - t0
+            kernel_ms, alloc_ms = tg.setup_timing()
+            rep_piv = [tg.setup_status(d) for d in range(D)]
+            tg.close()
+            if best is None or kernel_ms < best["kernel_seconds"] * 1e3:
+                flop = (5 if mode == "stable" else 6) * float(n) ** 3 * D
+                tf = flop / (kernel_ms * 1e-3) * 1e-12
+                best = {"kernel_seconds": kernel_ms * 1e-3, "cudaMalloc_seconds": alloc_ms * 1e-3, "create_wall_seconds": wall,
+                        "nominal_TFLOP": flop * 1e-12, "repaired_pivots": [int(sum(r[0] for r in rep_piv)), int(sum(r[1] for r in rep_piv))],
+                        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_tflops"],
+                                     "kernel": "gemm_f64_dmma_big_kernel (Cholesky trailing updates, triangular products, m and K products)",
+                                     "peak_source": peaks["fp64_src"],
+                                     "note": "nominal %dn^3 flop per dimension; device time from the covariance build to the band tables (CUDA events), allocations excluded" % (5 if mode == "stable" else 6)}}
+        out["modes"][mode] = best
+    out["clocks"] = sampler.stop()
+    return out
+
+
+def section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, chains_total, iters, leapfrog=10):
+    """BASELINE config 5: FN n=201, chains_total chains split over the ranks, on-device HMC (no hot-path collective; the
+    warm-up's pooled statistics and the final all-gather of the draws run in-library over NCCL), R-hat / ESS on rank 0."""
+    from manifold_constrained_gaussian_process_inference_b200 import distributed as Dm
+    first, n_local = Dm.shard_chains(chains_total, rank, world)
+    work = synthetic.make_workload("fn201", chains_total, rank=0)     # the same global population on every rank; each keeps its slice
+    tg = pkg.MagiTarget.from_config(work["yobs"], work["tvec"], work["phi"], pkg.fn_system(), work["sigma_init"], bandsize=20, jitter=1e-6,
+                                    setup_mode="stable", device=local, max_chains=n_local)
+    if world > 1:
+        Dm.init_device_comm(tg)                              # NCCL communicator inside the library, warmed
+    params = work["params"][first:first + n_local]
+    n_adapt = iters // 2
+    st = torch.cuda.current_stream().cuda_stream
+    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if sampler:
+        sampler.start()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    _, stt = pkg.run_hmc_sampler(tg, params, n_samples=iters, n_adapts=n_adapt, initial_step_size=0.002, n_leapfrog=leapfrog,
+                                 seed=20251018 + 5, chain_id_offset=first, keep_on_device=True, n_chains_total=chains_total, stream=st)
+    e1.record()
+    if world > 1:
+        full = Dm.allgather_draws_device(tg, stream=st)
+    else:
+        full = Dm.device_draws_as_tensor(tg)
+    e2.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), float(stt["grad_evals"])], dtype=torch.float64, device=dev)
+    tmax, tsum = t.clone(), t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    res = None
+    if rank == 0:
+        d = full[:, :: max(1, full.shape[1] // 512)][:, :512].cpu().numpy()      # R-hat / ESS on 512 chains spread over all ranks' shards
+        names = ["theta_a", "theta_b", "theta_c", "sigma_1", "sigma_2", "lp"]
+        summ = pkg.diagnostics.summarize(d, names=names)
+        sample_s, gather_ms, evals = float(tmax[0]) * 1e-3, float(tmax[1]), float(tsum[2])
+        gathered_bytes = int(full.numel() * 8)
+        res = {"config": {"workload": "fn201 cfg5: fn n=201 D=2 k=3 band=20, %d chains over %d GPU(s), HMC %d iterations (%d warm-up) x %d leapfrog steps" % (chains_total, world, iters, n_adapt, leapfrog),
+                          "chains_total": chains_total, "chains_per_gpu": n_local, "scaling": "strong"},
+               "metric": "leapfrog grad evals/sec (all chains)", "value": evals / sample_s, "unit": "evals/s", "n_gpus": world,
+               "sample_seconds": sample_s, "grad_evals": evals, "allgather_ms": gather_ms, "allgather_bytes": gathered_bytes,
+               "allgather_GBps": (gathered_bytes / (gather_ms * 1e-3) * 1e-9) if world > 1 and gather_ms > 0 else None,
+               "draws": list(full.shape), "accept_rate_median": float(np.median(stt["accept_rate"])),
+               "posterior_mean": {nm: r["mean"] for nm, r in zip(names, summ)}, "rhat": {nm: r["rhat"] for nm, r in zip(names, summ)},
+               "ess_bulk_512_chains": {nm: r["ess_bulk"] for nm, r in zip(names, summ)}, "theta_true": [0.2, 0.2, 3.0], "clocks": clocks,
+               "how": "CUDA events on the sampler's stream around the whole run (warm-up included) and around the all-gather; max over ranks"}
+    tg.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -119,6 +262,10 @@ def main():
     ap.add_argument("--bandsize", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--repeats", type=int, default=20, help="repetitions of the timed block of --steps launches")
+    ap.add_argument("--sections", default="dense,setup,cfg5", help="extra measurements of the own arm (comma list or 'none')")
+    ap.add_argument("--cfg5-chains", type=int, default=65536)
+    ap.add_argument("--cfg5-iters", type=int, default=240, help="HMC iterations of the cfg5 section (half of them warm-up)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -131,7 +278,7 @@ def main():
     n, D, k, b = work["n"], work["D"], work["k"], work["bandsize"]
     P = n * D + k + D
     config = {"workload": "%s: %s n=%d D=%d k=%d band=%d matern52 jitter=1e-6, %d chains/GPU, sigma sampled" % (args.workload, work["model"], n, D, k, b, chains),
-              "chains_per_gpu": chains, "n_times": n, "bandsize": b, "sharding": "chains across ranks, no data-path collective"}
+              "chains_per_gpu": chains, "n_times": n, "bandsize": b, "sharding": "chains across ranks, no data-path collective"}     # identical in both arms
 
     if args.impl == "reference":
         if rank != 0:
@@ -142,7 +289,7 @@ def main():
         for d in range(D):
             g = mo.calculate_gp_covariances(mo.MATERN52, work["phi"][:, d], work["tvec"], b, jitter=1e-6, setup_mode="stable")
             tables.append((g.CinvBand, g.mphiBand, g.KinvBand))
-        res = cpu_arm(work, tables, args.steps, warmup, chains)
+        res = cpu_arm(work, tables, args.steps, warmup, chains, nthreads=host_cores())
         val = res["evals_per_s"]
         out = {"impl": "reference", "metric": "leapfrog grad evals/sec (all chains)", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
                "steps": res["passes"], "warmup": warmup, "ms_per_step": res["seconds"] / res["passes"] * 1e3, "higher_is_better": True,
@@ -170,7 +317,7 @@ def main():
     psets = [(host.to(dev) + (1e-6 * s)).contiguous() for s in range(nsets)]
     gsets = [torch.empty_like(psets[0]) for _ in range(nsets)]
     lsets = [torch.empty(chains, dtype=torch.float64, device=dev) for _ in range(nsets)]
-    config["l2"] = "rotating %d input/output sets (%.0f MB) > 126 MB L2, no explicit flush" % (nsets, nsets * bytes_per_set / 1e6)
+    l2_note = "rotating %d input/output sets (%.0f MB) > 126 MB L2, no explicit flush" % (nsets, nsets * bytes_per_set / 1e6)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(i):
@@ -186,20 +333,26 @@ def main():
     if sampler:
         sampler.start()
     l0 = tg.launch_count()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(warmup + i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = tg.launch_count() - l0
+    reps = max(1, args.repeats)
+    rep_ms = []
+    for r in range(reps):                                   # each repetition: barrier + sync, EXACTLY --steps launches between two events
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(warmup + r * args.steps + i)
+        e1.record()
+        torch.cuda.synchronize()
+        rep_ms.append(e0.elapsed_time(e1))
+    launches = (tg.launch_count() - l0) // reps
+    t = torch.tensor(rep_ms, dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)            # per repetition: the slowest rank
+    rep_ms = sorted(float(x) for x in t.cpu())
+    ms = rep_ms[len(rep_ms) // 2] if len(rep_ms) % 2 else 0.5 * (rep_ms[len(rep_ms) // 2 - 1] + rep_ms[len(rep_ms) // 2])
 
     # ---- e2e: the public host API (HOST buffers in, HOST buffers out; copies inside the timed region) ----
     # The pinned buffers are allocated, and the calls are made, from the CPUs NVML reports as local to this GPU (what
@@ -245,8 +398,23 @@ def main():
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)          # the CPU baseline below uses every host core
 
+    wanted = [x for x in args.sections.split(",") if x and x != "none"]
+    extra = {}
+    peaks = load_peaks()
+    del psets, gsets, lsets
+    torch.cuda.empty_cache()
+    if rank == 0 and "dense" in wanted:
+        extra["dense"] = section_dense(pkg, synthetic, torch, dev, local, peaks)
+    if rank == 0 and "setup" in wanted:
+        extra["setup"] = section_setup(pkg, torch, local, peaks)
+        torch.cuda.empty_cache()
+    if "cfg5" in wanted:
+        if world > 1:
+            dist.barrier()
+        r5 = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, args.cfg5_chains, args.cfg5_iters)
+        if rank == 0:
+            extra["cfg5"] = r5
     if rank == 0:
-        peaks = load_peaks()
         value = world * chains * args.steps / (ms * 1e-3)
         per_launch_s = ms * 1e-3 / args.steps
         flops = synthetic.algorithmic_flops_per_eval(n, D, b)
@@ -264,6 +432,8 @@ def main():
         out = {"metric": "leapfrog grad evals/sec (all chains)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": int(launches), "clocks": clocks,
+               "timing": {"repeats": reps, "steps_per_repeat": args.steps, "ms_per_step_median": ms / args.steps, "ms_per_step_min": rep_ms[0] / args.steps,
+                          "ms_per_step_max": rep_ms[-1] / args.steps, "l2": l2_note, "how": "CUDA events around each block of --steps launches, max over ranks per block, median over blocks"},
                "e2e": {"value": world * chains * e2e_steps / e2e_dt, "unit": "evals/s", "h2d_bytes_per_step": chains * P * 8,
                        "d2h_bytes_per_step": chains * (P + 1) * 8, "steps": e2e_steps, "api": "magi_logdensity_and_gradient_batched (pinned host buffers)"},
                "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_tflops"],
@@ -274,13 +444,13 @@ def main():
                                 "algorithmic_bytes_per_eval": abytes, "peak_source": peaks["hbm_src"]}}
         if world == 1 and not args.no_cpu_baseline:
             tables = [(tg.get_band_table(d, "CinvBand"), tg.get_band_table(d, "mphiBand"), tg.get_band_table(d, "KinvBand")) for d in range(D)]
-            res = cpu_arm(work, tables, 1, 1, chains, min_seconds=args.cpu_seconds)
+            res = cpu_arm(work, tables, 1, 1, chains, nthreads=host_cores(), min_seconds=args.cpu_seconds)
             out["cpu_baseline"] = {"value": res["evals_per_s"], "unit": "evals/s", "cores": res["cores"], "kind": "port",
                                    "sample": "%d passes over the %d-chain batch in %.1f s (C restatement of the reference loop, OpenMP over chains, same band tables)" % (res["passes"], chains, res["seconds"])}
             # parity spot check of the measured kernel against the CPU arm (not timed)
-            ll_gpu = lsets[0].cpu().numpy()
             ll0, _ = tg.logdensity_and_gradient_batched(work["params"][:64])
             out["parity_ll_max_rel_err_vs_cpu"] = float(np.max(np.abs(ll0 - res["ll"][:64]) / np.abs(res["ll"][:64])))
+        out.update(extra)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

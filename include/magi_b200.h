@@ -42,8 +42,11 @@ typedef enum {
     MAGI_ERR_NOT_POSITIVE_DEFINITE = 5
 } magi_status;
 
-/* kernel ids: src/kernels.jl:74-81 (matern52), :42-50 (rbf) */
-enum { MAGI_KERNEL_MATERN52 = 0, MAGI_KERNEL_RBF = 1 };
+/* kernel ids: src/kernels.jl:74-81 (matern52), :42-50 (rbf), :109-118 (general Matern, nu = 1/2, 3/2, 5/2 in closed form).
+ * The reference has analytic time derivatives for Matern52Kernel and SqExponentialKernel only; every other base kernel --
+ * MaternKernel(nu) included, even at nu = 5/2 -- gets C but zero derivatives, i.e. the fallback m = 0, K = eI, Kinv = I/e
+ * (src/gaussian_process.jl:278-280, 319-331).  The three MATERN_NU* ids reproduce that behaviour. */
+enum { MAGI_KERNEL_MATERN52 = 0, MAGI_KERNEL_RBF = 1, MAGI_KERNEL_MATERN_NU12 = 2, MAGI_KERNEL_MATERN_NU32 = 3, MAGI_KERNEL_MATERN_NU52 = 4 };
 
 /* compiled ODE model registry (user callbacks cannot cross a C ABI into a kernel); src/ode_models.jl */
 enum {
@@ -122,6 +125,10 @@ int magi_set_band_tables(magi_handle* h, int dim, int which, const double* in);
 /* status of the device setup for one dimension: repaired (non-positive) pivots seen in chol(C+eI), chol(K+eI) */
 int magi_setup_status(magi_handle* h, int dim, int* repaired_pivots_c, int* repaired_pivots_k);
 
+/* where the time of the device setup inside magi_create went: device time from the covariance build to the band tables (K3-K6,
+ * CUDA events on the handle's stream) and host time spent in cudaMalloc for the GPCov fields and the work space */
+int magi_setup_timing(const magi_handle* h, double* kernel_ms, double* alloc_ms);
+
 /* Stand-alone GPCov for ONE dimension, computed on the GPU: replaces calculate_gp_covariances!(gp_cov, kernel, phi, tvec,
  * bandsize; complexity, jitter) (src/gaussian_process.jl:219-363).  phi = [variance, lengthscale]; outputs (any may be
  * NULL): seven dense n x n column-major matrices and three (2b+1) x n band tables; repaired[2] = repaired pivot counts. */
@@ -148,6 +155,18 @@ int magi_hmc_init(magi_handle* h, int n_chains, const double* params0 /* P x n_c
  * (device pointer, number of doubles, cudaStream_t, user) for the pooled window statistics of the warm-up; returns 0 on success */
 typedef int (*magi_allreduce_fn)(void* dev_ptr, long long n_doubles, void* stream, void* user);
 int magi_hmc_set_global(magi_handle* h, long long n_chains_total, magi_allreduce_fn allreduce, void* user);
+/* In-library collectives of a multi-rank run (NCCL over NVLink, resolved from libnccl.so.2 at run time).  Rank 0 calls
+ * magi_nccl_unique_id and distributes the MAGI_NCCL_ID_BYTES bytes by any host-side means; every rank then calls magi_comm_init
+ * (collective).  A host that already has an ncclComm_t on the handle's device hands it over with magi_comm_attach instead (the
+ * host keeps ownership).  With a communicator set and no callback given to magi_hmc_set_global, magi_hmc_run sums the warm-up's
+ * pooled window statistics with ncclAllReduce on its stream; magi_hmc_allgather_draws gathers the retained draws of all ranks:
+ * out_dev is [world][n_stored][n_chains][n_cols] on the device, all ranks holding equally many chains and iterations. */
+#define MAGI_NCCL_ID_BYTES 128
+int magi_nccl_unique_id(char* id /* MAGI_NCCL_ID_BYTES */);
+int magi_comm_init(magi_handle* h, const char* id, int rank, int world);
+int magi_comm_attach(magi_handle* h, void* nccl_comm, int rank, int world);
+int magi_comm_warmup(magi_handle* h, void* stream);
+int magi_hmc_allgather_draws(magi_handle* h, double* out_dev, void* stream);
 int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream);
 int magi_hmc_reset_stats(magi_handle* h);
 int magi_hmc_get_state(magi_handle* h, double* params /* P x n_chains or NULL */, double* ll /* n_chains or NULL */);

@@ -4,7 +4,7 @@ include/magi_b200.h); this package is the host-side mirror of the reference inte
 (MagiJl.jl: GPCov / calculate_gp_covariances!, MagiTarget, dimension / logdensity / logdensity_and_gradient,
 run_nuts_sampler-shaped batched HMC, solve_magi)."""
 from . import _lib
-from .kernels import Kernel, create_matern52_kernel, create_rbf_kernel
+from .kernels import Kernel, create_general_matern_kernel, create_matern52_kernel, create_rbf_kernel
 from .ode_models import OdeSystem, get_ode_system, fn_system, hes1_system, lv_system, MODEL_IDS
 from .gaussian_process import GPCov, calculate_gp_covariances, mat2band
 from .samplers import run_hmc_sampler
@@ -13,7 +13,7 @@ from . import diagnostics, distributed, initialization
 from .target import MagiTarget, dimension, capabilities, logdensity, logdensity_and_gradient, LogDensityOrder
 
 __all__ = [
-    "Kernel", "create_matern52_kernel", "create_rbf_kernel", "OdeSystem", "get_ode_system", "fn_system", "hes1_system",
+    "Kernel", "create_matern52_kernel", "create_rbf_kernel", "create_general_matern_kernel", "OdeSystem", "get_ode_system", "fn_system", "hes1_system",
     "lv_system", "MODEL_IDS", "GPCov", "calculate_gp_covariances", "mat2band", "MagiTarget", "dimension", "capabilities",
     "logdensity", "logdensity_and_gradient", "LogDensityOrder", "run_hmc_sampler", "solve_magi", "diagnostics", "distributed",
 ]

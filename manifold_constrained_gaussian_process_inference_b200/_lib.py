@@ -29,7 +29,7 @@ class MagiConfig(ctypes.Structure):
 
 # status codes / enums of include/magi_b200.h
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NOT_READY, ERR_UNSUPPORTED, ERR_NOT_POSITIVE_DEFINITE = range(6)
-KERNEL_MATERN52, KERNEL_RBF = 0, 1
+KERNEL_MATERN52, KERNEL_RBF, KERNEL_MATERN_NU12, KERNEL_MATERN_NU32, KERNEL_MATERN_NU52 = range(5)
 SETUP_REFERENCE_ORDER, SETUP_STABLE, SETUP_INJECT = 0, 1, 2
 MAT_C, MAT_CINV, MAT_CPRIME, MAT_CDOUBLEPRIME, MAT_MPHI, MAT_KPHI, MAT_KINV, MAT_CINV_BAND, MAT_MPHI_BAND, MAT_KINV_BAND = range(10)
 LAYOUT_CHAIN_CONTIGUOUS = 0
@@ -46,7 +46,8 @@ EXPORTED = [
     "magi_logdensity_and_gradient_batched_dev", "magi_get_matrix", "magi_set_band_tables", "magi_setup_status",
     "magi_launch_count", "magi_gp_covariances", "magi_gp_nlml_batched", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
     "magi_hmc_get_state", "magi_hmc_get_draws", "magi_hmc_draws_dev", "magi_hmc_get_stats", "magi_hmc_grad_evals",
-    "magi_hmc_set_global",
+    "magi_hmc_set_global", "magi_setup_timing", "magi_nccl_unique_id", "magi_comm_init", "magi_comm_attach", "magi_comm_warmup",
+    "magi_hmc_allgather_draws",
 ]
 
 
@@ -72,6 +73,7 @@ def lib():
     L.magi_get_matrix.argtypes = [vp, ci, ci, dp]
     L.magi_set_band_tables.argtypes = [vp, ci, ci, dp]
     L.magi_setup_status.argtypes = [vp, ci, c_int_p, c_int_p]
+    L.magi_setup_timing.argtypes = [vp, dp, dp]
     L.magi_launch_count.argtypes = [vp]
     L.magi_launch_count.restype = ctypes.c_longlong
     for name in dir(L):
@@ -99,6 +101,12 @@ def _optional(L):
         L.magi_hmc_get_stats.argtypes = [vp, dp, dp, c_int_p, dp, dp]
         L.magi_hmc_grad_evals.argtypes = [vp]
         L.magi_hmc_grad_evals.restype = ll
+    if hasattr(L, "magi_comm_init"):
+        L.magi_nccl_unique_id.argtypes = [ctypes.c_char_p]
+        L.magi_comm_init.argtypes = [vp, ctypes.c_char_p, ci, ci]
+        L.magi_comm_attach.argtypes = [vp, vp, ci, ci]
+        L.magi_comm_warmup.argtypes = [vp, vp]
+        L.magi_hmc_allgather_draws.argtypes = [vp, vp, vp]
     if hasattr(L, "magi_hmc_set_global"):
         L.magi_hmc_set_global.argtypes = [vp, ctypes.c_longlong, ALLREDUCE_FN, vp]
 

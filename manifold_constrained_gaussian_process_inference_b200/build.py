@@ -42,31 +42,29 @@ def _compile(src, extra):
 
 
 def build(force: bool = False, fast: bool = False, verbose: bool = False) -> str:
-    global OBJDIR
+    global OBJDIR, LIB
     if fast and "MAGI_OBJ_DIR" not in os.environ:
         OBJDIR = os.path.join(HERE, "build_fast")      # objects compiled with -DMAGI_FAST_BUILD must never be linked into a full build
+    if fast and "MAGI_LIB_NAME" not in os.environ:
+        LIB = os.path.join(LIBDIR, "libmagi_fast.so")  # ... and the development library never replaces the product library
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     extra = {"force": force, "defs": (["-DMAGI_FAST_BUILD"] if fast else []) + os.environ.get("MAGI_EXTRA_DEFS", "").split()}
     srcs = sources()
     if fast:   # development builds: only the FN / Hes1 / LV kernels (the full build adds the other models)
-        srcs = [s_ for s_ in srcs if not (s_.startswith("banded_inst_") and s_ not in ("banded_inst_0.cu", "banded_inst_1.cu", "banded_inst_7.cu"))]
+        keep = ("_inst_0.cu", "_inst_1.cu", "_inst_7.cu")
+        srcs = [s_ for s_ in srcs if not (s_.startswith(("banded_inst_", "flow_inst_")) and not s_.endswith(keep))]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         res = list(ex.map(lambda s: _compile(s, extra), srcs))
     objs = [o for o, _ in res]
     if any(ch for _, ch in res) or not os.path.exists(LIB) or force:
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lnccl"] if _has_nccl() else \
-              [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
         if verbose:
             print("linked", LIB)
     return LIB
-
-
-def _has_nccl() -> bool:
-    return False   # NCCL is used through torch.distributed (plumbing); the library itself has no collective
 
 
 if __name__ == "__main__":

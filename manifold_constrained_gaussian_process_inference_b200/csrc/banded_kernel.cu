@@ -29,7 +29,7 @@ size_t fragtab_doubles(int n, int b, int D) {
 
 __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const double* __restrict__ band_mphi,
                                      const double* __restrict__ band_kinv, double* __restrict__ fragtab,
-                                     int n, int b, int D, int HB, int NCH, int NT) {
+                                     int n, int b, int D, int HB, int NCH, int NT, int natural, double scale_c, double scale_k) {
     const int NP = (NT + 1) / 2;
     const size_t per_view = (size_t)D * NP * NCH * 64;
     const size_t total = 4 * per_view;
@@ -43,25 +43,29 @@ __global__ void build_fragtab_kernel(const double* __restrict__ band_cinv, const
         int view = (int)(r / D);
         const int J = 2 * p + tt;
         int gid = lane >> 2, q = lane & 3;
-        int o = 8 * J + (gid >> 1) + 4 * (gid & 1);
+        // windowed kernel: output slots permuted so that a C fragment is the next product's A fragment; dataflow kernel
+        // (flow_kernel.cuh): natural order, B[k = q][n = gid] = T[in = 4c + q][out = 8J + gid]
+        int o = natural ? 8 * J + gid : 8 * J + (gid >> 1) + 4 * (gid & 1);
         int i = 4 * (2 * J - HB + hh) + q;
         double v = 0.0;
         if (J >= 0 && J < NT && o < n && i >= 0 && i < n && abs(i - o) <= b) {
             const double* src = (view == 1) ? band_cinv : (view == 2 ? band_kinv : band_mphi);
             src += (size_t)d * tab;
             v = (view == 3) ? src[(size_t)(b + (o - i)) * n + i] : src[(size_t)(b + (i - o)) * n + o];
+            if (view == 1) v *= scale_c;        // 1/beta2 folded into C~, 1/beta1 into K~: the kernels never multiply by them
+            if (view == 2) v *= scale_k;
         }
         fragtab[idx] = v;
     }
 }
 
 cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
-                                 int n, int b, int D, cudaStream_t st) {
+                                 int n, int b, int D, bool natural, double scale_c, double scale_k, cudaStream_t st) {
     BandGeom g = band_geom(n, b);
     size_t total = fragtab_doubles(n, b, D);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT);
+    build_fragtab_kernel<<<blocks, 256, 0, st>>>(band_cinv, band_mphi, band_kinv, fragtab, n, b, D, g.HB, g.NCH, g.NT, natural ? 1 : 0, scale_c, scale_k);
     return cudaGetLastError();
 }
 
@@ -80,6 +84,54 @@ bool model_dims(int model, int& D, int& K) {
     case MAGI_MODEL_LV: D = 2; K = 4; return true;
     default: return false;
     }
+}
+
+// ---- dataflow K1 (flow_kernel.cuh): shared-memory footprint, wavefront order ----
+bool model_kx(int model, int& KX) {
+    switch (model) {
+    case MAGI_MODEL_FN: KX = Ode<MAGI_MODEL_FN>::KX; return true;
+    case MAGI_MODEL_HES1: KX = Ode<MAGI_MODEL_HES1>::KX; return true;
+    case MAGI_MODEL_HES1LOG: KX = Ode<MAGI_MODEL_HES1LOG>::KX; return true;
+    case MAGI_MODEL_HES1LOG_FIXG: KX = Ode<MAGI_MODEL_HES1LOG_FIXG>::KX; return true;
+    case MAGI_MODEL_HES1LOG_FIXF: KX = Ode<MAGI_MODEL_HES1LOG_FIXF>::KX; return true;
+    case MAGI_MODEL_HIV: KX = Ode<MAGI_MODEL_HIV>::KX; return true;
+    case MAGI_MODEL_PTRANS: KX = Ode<MAGI_MODEL_PTRANS>::KX; return true;
+    case MAGI_MODEL_LV: KX = Ode<MAGI_MODEL_LV>::KX; return true;
+    default: return false;
+    }
+}
+
+// layout of flow_logpost_kernel's shared memory (G = 2: 16 chains per block)
+size_t flow_smem_bytes(int D, int K, int KX, int n, int HB, int& RS0) {
+    const int NT = (n + 7) / 8, NP = (NT + 1) / 2, CH = 16, RED = 3 + K;
+    RS0 = (16 * NP + 8 * HB + 15) / 16 * 16;
+    const size_t doubles = (size_t)3 * CH * D * RS0 + (size_t)D * NP * CH * RED + (size_t)2 * CH * (KX + 3 * D) + (size_t)CH * D * (RED + 4) + (size_t)D * 16 * NP;
+    if (NP > 32) return (size_t)1 << 40;          // the final stage gives one lane to every tile pair
+    return doubles * sizeof(double) + (size_t)2 * D * NP * sizeof(unsigned long long) + 16 + (size_t)3 * D * NP * sizeof(int);
+}
+
+// Order in which the warps draw the units (sweep s, dimension d, pair p).  Every unit a unit waits for comes strictly
+// earlier in the list (S2 reads E of pairs p - HP .. p + HP, S3 reads KE of the same range and of the other dimensions), so
+// drawing tickets in this order cannot deadlock.  extra_lag < 0: sweep after sweep (all S1, all S2, all S3) -- with 16 warps
+// in flight a unit's producers are then long finished when its ticket is drawn.  extra_lag >= 0: a wavefront along the time
+// axis (S1 of pair tau, S2 of pair tau - lag, S3 of pair tau - 2 lag with lag = HP + 1 + extra_lag), measured slower:
+// producers and consumers a few tickets apart run concurrently and the consumers wait.
+std::vector<int> flow_unit_order(int D, int NP, int HB, int extra_lag) {
+    std::vector<int> u;
+    if (extra_lag < 0) {
+        for (int s = 0; s < 3; ++s)
+            for (int p = 0; p < NP; ++p)
+                for (int d = 0; d < D; ++d) u.push_back(s | (d << 2) | (p << 8));
+        return u;
+    }
+    const int HP = (4 * HB + 15) / 16, lag = HP + 1 + extra_lag;
+    for (int tau = 0; tau < NP + 2 * lag; ++tau)
+        for (int s = 2; s >= 0; --s) {                      // the oldest (and heaviest) work of a wavefront step first
+            const int p = tau - s * lag;
+            if (p < 0 || p >= NP) continue;
+            for (int d = 0; d < D; ++d) u.push_back(s | (d << 2) | (p << 8));
+        }
+    return u;
 }
 
 size_t banded_scratch_doubles_per_cta(int G, int D, int NT) { return (size_t)G * D * NT * 64; }   // Ke
@@ -116,7 +168,8 @@ void banded_pick_config(int D, int K, int NT, int HB, int smem_limit, int gmax, 
 }
 
 // one translation unit per model instantiates the kernels (banded_inst_*.cu), so they compile in parallel
-#define MAGI_DECL_MODEL(M) cudaError_t launch_banded_model_##M(const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st);
+#define MAGI_DECL_MODEL(M) cudaError_t launch_banded_model_##M(const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st); \
+                           cudaError_t launch_flow_model_##M(const FlowArgs& a, int HB, int grid, size_t smem_bytes, cudaStream_t st);
 MAGI_DECL_MODEL(0) MAGI_DECL_MODEL(1) MAGI_DECL_MODEL(2) MAGI_DECL_MODEL(3) MAGI_DECL_MODEL(4) MAGI_DECL_MODEL(5) MAGI_DECL_MODEL(6) MAGI_DECL_MODEL(7)
 #undef MAGI_DECL_MODEL
 // `a.G`, `a.scratch_in_smem` must come from banded_pick_config; DW = blockDim warps / G.
@@ -131,6 +184,22 @@ cudaError_t launch_banded_cfg(int model, const BandedArgs& a, int HB, int DW, si
     case MAGI_MODEL_HES1LOG_FIXF: return launch_banded_model_4(a, HB, DW, smem_bytes, st);
     case MAGI_MODEL_HIV: return launch_banded_model_5(a, HB, DW, smem_bytes, st);
     case MAGI_MODEL_PTRANS: return launch_banded_model_6(a, HB, DW, smem_bytes, st);
+#endif
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_flow_cfg(int model, const FlowArgs& a, int HB, int grid, size_t smem_bytes, cudaStream_t st) {
+    switch (model) {
+    case MAGI_MODEL_FN: return launch_flow_model_0(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_HES1: return launch_flow_model_1(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_LV: return launch_flow_model_7(a, HB, grid, smem_bytes, st);
+#ifndef MAGI_FAST_BUILD
+    case MAGI_MODEL_HES1LOG: return launch_flow_model_2(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_HES1LOG_FIXG: return launch_flow_model_3(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_HES1LOG_FIXF: return launch_flow_model_4(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_HIV: return launch_flow_model_5(a, HB, grid, smem_bytes, st);
+    case MAGI_MODEL_PTRANS: return launch_flow_model_6(a, HB, grid, smem_bytes, st);
 #endif
     default: return cudaErrorInvalidValue;
     }

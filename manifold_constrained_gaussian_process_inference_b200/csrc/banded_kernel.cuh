@@ -23,71 +23,10 @@
 #include <cstdlib>
 #include <type_traits>
 #include "magi_common.cuh"
+#include "k1_primitives.cuh"
 #include "ode_models.cuh"
 
 namespace magi {
-
-// ------------------------------------------------------------------------------------------------------------
-// K1
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double quad_sum(double v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
-
-// ---- TMA bulk copy + mbarrier helpers (fragment ring) ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done = 0;
-#pragma unroll 1
-    for (unsigned it = 0; it < (1u << 22); ++it) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-// waits for two barriers at once (the two try_wait round trips overlap)
-__device__ __forceinline__ void mbar_wait2(unsigned long long* bar_a, unsigned parity_a, unsigned long long* bar_b, unsigned parity_b) {
-    unsigned da = 0, db = 0;
-#pragma unroll 1
-    for (unsigned it = 0; it < (1u << 22); ++it) {
-        asm volatile("{\n.reg .pred p;\n.reg .pred r;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\nmbarrier.try_wait.parity.shared::cta.b64 r, [%4], %5;\n"
-                     "selp.u32 %0, 1, 0, p;\nselp.u32 %1, 1, 0, r;\n}\n"
-                     : "=r"(da), "=r"(db) : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b) : "memory");
-        if (da & db) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
-
-__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
-}
-
-// calls f(std::integral_constant<int, d>) for the runtime (warp-uniform) dimension d: the model functors then see a
-// compile-time dimension and compile to straight-line code
-template <int D, class F> __device__ __forceinline__ void dispatch_dim(int d, F& f) {
-    if constexpr (D >= 1) { if (d == 0) { f(std::integral_constant<int, 0>{}); return; } }
-    if constexpr (D >= 2) { if (d == 1) { f(std::integral_constant<int, 1>{}); return; } }
-    if constexpr (D >= 3) { if (d == 2) { f(std::integral_constant<int, 2>{}); return; } }
-    if constexpr (D >= 4) { if (d == 3) { f(std::integral_constant<int, 3>{}); return; } }
-    if constexpr (D >= 5) { if (d == 4) { f(std::integral_constant<int, 4>{}); return; } }
-}
 
 // Warp-specialised K1 (v13).  One block = G chain-groups (8 chains each) x D dimensions = G*D tasks; every task has a DMMA
 // warp ("C") and a pointwise warp ("P"), 2*G*D <= 16 warps, <= 128 registers, one block per SM.  Operand windows (x, e, Ke)
@@ -162,7 +101,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
     const long long chain = (long long)blockIdx.x * (G * 8) + g * 8 + gid;
     const bool cvalid = chain < a.n_chains;
     const double* xp = a.params + (cvalid ? chain : (long long)a.n_chains - 1) * a.pitch;
-    const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
+    const double inv_b3 = a.inv_beta[2];
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
     long long wq = 0, wfull = 0;                 // MAGI_DBG_WAITS: cycles spent waiting on the queues / the fragment ring
     if (a.dbg) tk0 = clock64();
@@ -359,7 +298,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                     for (int pt = 0; pt < 2; ++pt) {
                         acc_xcx += xw[HB + 2 * tt + pt] * c[tt][pt];
-                        xs[(2 * tt + pt) * 32] = um[tt][pt] * inv_b1 - c[tt][pt] * inv_b2;
+                        xs[(2 * tt + pt) * 32] = um[tt][pt] - c[tt][pt];      // 1/beta1, 1/beta2 are folded into the K~ and C~ fragment tables
                     }
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(q2full + qs); mbar_arrive(bempty + st); }
@@ -523,8 +462,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 for (int tt = 0; tt < 2; ++tt)
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) {
-                        wv[tt][0][dd] = wsrc[((size_t)dd * NT + tt) * 64] * inv_b1;         // likelihoods.jl:201
-                        wv[tt][1][dd] = wsrc[((size_t)dd * NT + tt) * 64 + 32] * inv_b1;
+                        wv[tt][0][dd] = wsrc[((size_t)dd * NT + tt) * 64];                  // likelihoods.jl:201 (the scratch holds Ke / beta1)
+                        wv[tt][1][dd] = wsrc[((size_t)dd * NT + tt) * 64 + 32];
                     }
             } else {
 #pragma unroll
@@ -533,8 +472,8 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) {
                         const double* wsrc = kscr + ((size_t)(g * D + dd) * NT + (J < 0 ? 0 : J)) * 64 + lane;
-                        wv[tt][0][dd] = (J < 0) ? 0.0 : wsrc[0] * inv_b1;  // likelihoods.jl:201
-                        wv[tt][1][dd] = (J < 0) ? 0.0 : wsrc[32] * inv_b1;
+                        wv[tt][0][dd] = (J < 0) ? 0.0 : wsrc[0];           // likelihoods.jl:201
+                        wv[tt][1][dd] = (J < 0) ? 0.0 : wsrc[32];
                     }
                 }
             }
@@ -587,7 +526,7 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
         if (q == 0) {
             double* r = red + ((size_t)(g * 8 + gid) * D + d) * RED;
             r[2] = acc_sse;
-            r[3] = ((badm >> (gid * 4)) & 0xfu) ? 1.0 : 0.0;
+            r[3] = (((badm >> (gid * 4)) & 0xfu) && a.grad != nullptr) ? 1.0 : 0.0;    // value-only calls look at ll alone (interface.jl:155-160)
 #pragma unroll
             for (int i = 0; i < K; ++i) r[4 + i] = gth[i];
         }
@@ -644,13 +583,13 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
                 double ll_obs = -0.5 * sse / s2;                      // likelihoods.jl:139
                 if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);   // :141
                 ll += ll_obs / a.beta[2];                             // :143
-                ll += (-0.5 * eke) / a.beta[0];                       // :146-147
-                ll += (-0.5 * xcx) / a.beta[1];                       // :150-151
+                ll += -0.5 * eke;                                     // :146-147 (1/beta1 folded into K~)
+                ll += -0.5 * xcx;                                     // :150-151 (1/beta2 folded into C~)
                 gsig[d] = (s > 0 && nobs > 0) ? (sse / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
-                bad |= !isfinite(gsig[d]);
+                if (gp) bad |= !isfinite(gsig[d]);
             }
 #pragma unroll
-            for (int i = 0; i < K; ++i) bad |= !isfinite(gthf[i]);
+            for (int i = 0; i < K; ++i) if (gp) bad |= !isfinite(gthf[i]);
             bad |= !isfinite(ll);
             if (bad) {                                                // interface.jl:222-226
                 a.ll[c] = -INFINITY;
@@ -684,11 +623,10 @@ __global__ void __launch_bounds__(512, 1) banded_logpost_kernel(const BandedArgs
 template <int MODEL, int HB>
 static cudaError_t launch_one(const BandedArgs& a, int DW, size_t smem_bytes, cudaStream_t st) {
     auto kern = banded_logpost_kernel<MODEL, HB>;
-    static bool attr_set = false;    // per instantiation
-    if (!attr_set) {
+    static PerDeviceOnce once;       // per instantiation
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int threads = 2 * a.G * DW * 32;      // one DMMA warp and one pointwise warp per (chain-group, dimension) task
     const int blocks = (a.n_chains + a.G * 8 - 1) / (a.G * 8);

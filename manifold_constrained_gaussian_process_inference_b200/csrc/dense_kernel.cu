@@ -75,14 +75,14 @@ template <int MODEL>
 __global__ void dense_e_kernel(const double* __restrict__ params, long long pitch, int n, int D, int n_chains,
                                const double* MX, double* E) {   // E may alias MX (in place)
     constexpr int K = DenseOde<MODEL>::K;
-    const int c = blockIdx.y;
+    const int c = blockIdx.x;                    // chains on grid.x: no 65535 limit
     const double* xp = params + (size_t)c * pitch;
     double th[DenseOde<MODEL>::KX];
 #pragma unroll
     for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
     DenseOde<MODEL>::prepare(th);
     const size_t plane = (size_t)n * n_chains;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
         for (int d = 0; d < D; ++d) {
             const size_t o = (size_t)d * plane + (size_t)c * n + i;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) 
             eke += Ed[i] * ke;
             xcx += xdv * cx;
             sse += e0 * e0;
-            bad |= !isfinite(gv);
+            bad |= gp && !isfinite(gv);            // value-only calls look at the log density alone (interface.jl:155-160)
             if (gp) gp[(size_t)d * n + i] = gv;
         }
         eke = block_sum(eke, sh); xcx = block_sum(xcx, sh); sse = block_sum(sse, sh);
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) 
         ll += (-0.5 * eke) / a.beta[0];
         ll += (-0.5 * xcx) / a.beta[1];
         const double gsig = (s > 0 && nobs > 0) ? (sse / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
-        bad |= !isfinite(gsig);
+        bad |= gp && !isfinite(gsig);
         if (!a.sigma_is_fixed) {
             const double gls = gsig * s + 1.0;                         // interface.jl:249-253
             bad2 |= !isfinite(gls);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) 
         }
     }
 #pragma unroll
-    for (int i = 0; i < K; ++i) { gth[i] = block_sum(gth[i], sh); bad |= !isfinite(gth[i]); }
+    for (int i = 0; i < K; ++i) { gth[i] = block_sum(gth[i], sh); bad |= gp && !isfinite(gth[i]); }
     bad |= !isfinite(ll);
     if (bad) atomicOr(&sbad, 1);
     if (bad2) atomicOr(&sbad, 2);
@@ -212,7 +212,7 @@ template <int MODEL>
 static int dense_pointwise(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad,
                            const double* MX, double* E, const double* KE, const double* CX, const double* MT, int stage, cudaStream_t st) {
     if (stage == 0) {
-        dim3 grid((h->n + 255) / 256, n_chains);
+        dim3 grid(n_chains, (h->n + 255) / 256);
         dense_e_kernel<MODEL><<<grid, 256, 0, st>>>(params, pitch, h->n, h->D, n_chains, MX, E);
     } else {
         DenseGradArgs a;

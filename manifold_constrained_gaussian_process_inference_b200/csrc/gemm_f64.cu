@@ -296,11 +296,10 @@ template <bool AK, bool BKC>
 static cudaError_t launch_big(const GemmArgs& g, int batch, cudaStream_t st) {
     auto kern = gemm_f64_dmma_big_kernel<AK, BKC>;
     const size_t smem = sizeof(double) * 2 * BG_ST * BG_TILE;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;       // per instantiation
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     dim3 grid((g.N + BG_BN - 1) / BG_BN, (g.M + BG_BM - 1) / BG_BM, batch);
     kern<<<grid, 512, smem, st>>>(g);
@@ -311,11 +310,10 @@ template <bool AK, bool BKC>
 static cudaError_t launch_streamk(const GemmArgs& g, int tiles_m, int tiles_n, int batch, int blocks, cudaStream_t st) {
     auto kern = gemm_f64_dmma_streamk_kernel<AK, BKC>;
     const size_t smem = sizeof(double) * 2 * BG_ST * BG_TILE;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;       // per instantiation
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     kern<<<blocks, 512, smem, st>>>(g, tiles_m, tiles_n, batch);
     return cudaGetLastError();
@@ -362,8 +360,7 @@ cudaError_t launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return cudaSuccess;
     static const bool force_small = getenv("MAGI_GEMM_SMALL") != nullptr;
     static const bool no_streamk = getenv("MAGI_GEMM_NO_STREAMK") != nullptr;
-    static int sm_count = 0;
-    if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+    const int sm_count = g.sm_count > 0 ? g.sm_count : current_sm_count();      // of the device the caller launches on
     const bool a_ok = (g.rsA == 1 || g.csA == 1), b_ok = (g.rsB == 1 || g.csB == 1);
     const bool ak = (g.rsA != 1);          // A(m, k): unit stride along k unless rsA == 1 (m-contiguous)
     const bool bkc = (g.csB != 1);         // B(k, n): unit stride along k unless csB == 1 (n-contiguous)

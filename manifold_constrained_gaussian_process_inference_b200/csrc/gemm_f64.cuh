@@ -21,6 +21,7 @@ struct GemmArgs {
     double* sk_work = nullptr;
     unsigned* sk_flags = nullptr;
     unsigned sk_epoch = 0;
+    int sm_count = 0;     // SMs of the launch device (0: queried per launch)
 };
 constexpr int kStreamKSlots = 160;                       // >= SM count
 constexpr size_t kStreamKWorkDoubles = (size_t)kStreamKSlots * 128 * 128;

@@ -55,11 +55,24 @@ __device__ __forceinline__ double u01(unsigned int a, unsigned int b) {   // (0,
     const unsigned long long v = ((unsigned long long)a << 21) ^ (unsigned long long)b;   // 53 bits
     return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
 }
+// Philox key of a chain: (seed, global chain id) hashed TOGETHER (splitmix64 of the seed, plus the chain id, hashed again), so
+// that the streams of (seed s, chain c) and (seed s ^ k, chain c ^ k) are unrelated -- a key of `seed ^ chain` made runs with
+// nearby seeds reuse one permuted set of streams.  The counter words carry (pair | draw kind, stream, iteration).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long chain_key(unsigned long long seed, long long chain) {
+    return splitmix64(splitmix64(seed) + (unsigned long long)chain);
+}
 // two standard normals for (chain, iteration, pair index)
 __device__ __forceinline__ void normal_pair(unsigned long long seed, long long chain, long long iter, unsigned int pair, unsigned int stream,
                                             double& z0, double& z1) {
     unsigned int c[4] = {pair, stream, (unsigned int)iter, (unsigned int)(iter >> 32)};
-    philox4x32(c, (unsigned int)(seed ^ (unsigned long long)chain), (unsigned int)((seed >> 32) ^ ((unsigned long long)chain >> 32) ^ 0x5851F42Du));
+    const unsigned long long key = chain_key(seed, chain);
+    philox4x32(c, (unsigned int)key, (unsigned int)(key >> 32));
     const double u1 = u01(c[0], c[1]), u2 = u01(c[2], c[3]);
     const double r = sqrt(-2.0 * log(u1));
     double s, co;
@@ -153,8 +166,9 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
         if (isnan(a)) a = 0.0;
         double z0, z1;
         normal_pair(s.seed, c + s.chain_offset, s.iter, 0u, 1u, z0, z1);
-        unsigned int cc[4] = {1u, 2u, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};
-        philox4x32(cc, (unsigned int)(s.seed ^ (unsigned long long)(c + s.chain_offset)), (unsigned int)(s.seed >> 32) ^ 0x2545F491u);
+        unsigned int cc[4] = {1u, 2u, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};     // stream 2: the accept uniform
+        const unsigned long long key = chain_key(s.seed, c + s.chain_offset);
+        philox4x32(cc, (unsigned int)key, (unsigned int)(key >> 32));
         const double u = u01(cc[0], cc[1]);
         s_accept = (u < a) ? 1 : 0;
         s.acc_sum[c] += a;
@@ -370,9 +384,14 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
         if (in_slow) {
             s->wcount += s->n_chains_total;
             if (it + 1 == win_end) {
-                if (s->allreduce) {                               // sum of the per-slice sums over the ranks (in place, on this stream)
+                // sum of the per-slice sums over the ranks, in place, on this stream: ncclAllReduce on the handle's communicator
+                // (magi_comm_init / magi_comm_attach), or a host callback (magi_hmc_set_global) for transports other than NCCL
+                if (s->allreduce) {
                     int rc = s->allreduce(s->wpart, (long long)kWinSlices * 2 * P, (void*)st, s->allreduce_user);
                     if (rc) return set_error(MAGI_ERR_CUDA, "magi_hmc_run: the window all-reduce callback failed");
+                } else {
+                    int rc = comm_allreduce_sum(h, s->wpart, (size_t)kWinSlices * 2 * P, st);
+                    if (rc) return rc;
                 }
                 hmc_window_merge_kernel<<<(P + 127) / 128, 128, 0, st>>>(*s, P, s->wpart);
                 h->launches++;
@@ -424,6 +443,21 @@ extern "C" int magi_hmc_draws_dev(magi_handle* h, void** ptr, long long* n_store
     if (n_chains) *n_chains = s->n_chains;
     if (n_cols) *n_cols = s->n_draw_cols;
     return MAGI_OK;
+}
+
+// End-of-run all-gather of the retained draws over the handle's communicator: out_dev receives [world][n_stored][n_chains][n_cols]
+// (every rank must hold the same number of chains and of stored iterations); asynchronous on `stream`.
+extern "C" int magi_hmc_allgather_draws(magi_handle* h, double* out_dev, void* stream) {
+    if (!h || !h->hmc || !out_dev) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_allgather_draws: bad argument");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const size_t cnt = (size_t)s->n_draws * s->n_chains * s->n_draw_cols;
+    if (!h->nccl_comm || h->nccl_world <= 1) {
+        HCK(cudaMemcpyAsync(out_dev, s->draws, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, st), "copy draws");
+        return MAGI_OK;
+    }
+    return comm_allgather(h, s->draws, out_dev, cnt, st);
 }
 
 // per-chain statistics: mean acceptance probability, current step size, divergences; xmean = posterior mean of vec(X) per chain

@@ -38,8 +38,9 @@ extern "C" int magi_destroy(magi_handle* h) {
     free_dev(h->d_fragtab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
     free_dev(h->d_dense_work); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
-    free_dev(h->d_small); if (h->h_pin) cudaFreeHost(h->h_pin);
+    free_dev(h->d_small); free_dev(h->d_flow_units); if (h->h_pin) cudaFreeHost(h->h_pin);
     hmc_free(h);
+    comm_free(h);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 3; ++i) if (h->pipe_streams[i]) cudaStreamDestroy(h->pipe_streams[i]);
     delete h;
@@ -62,8 +63,10 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
     }
     if (cfg->setup_mode != MAGI_SETUP_INJECT) {
         if (!cfg->phi) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: phi is required unless setup_mode is MAGI_SETUP_INJECT");
-        if (cfg->kernel_id != MAGI_KERNEL_MATERN52 && cfg->kernel_id != MAGI_KERNEL_RBF)
+        if (cfg->kernel_id < MAGI_KERNEL_MATERN52 || cfg->kernel_id > MAGI_KERNEL_MATERN_NU52)
             return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_create: unknown kernel_id");
+        if (cfg->kernel_id > MAGI_KERNEL_RBF)        // gaussian_process.jl:278-280: a warning, then the zero-derivative fallback
+            g_last_error = "Time derivative calculation not implemented for this base kernel type. Derivatives will be zero.";
         for (int d = 0; d < cfg->n_dims; ++d) {   // src/MagiJl.jl:469-472
             double var = cfg->phi[2 * d], len = cfg->phi[2 * d + 1];
             if (!std::isfinite(var) || var <= 0 || !std::isfinite(len) || len <= 0)
@@ -130,6 +133,22 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
         size_t fsz = fragtab_doubles(h->n, h->b, h->D);
         if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
         banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, 4, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
+        // K1 variant: the windowed, warp-specialised kernel (banded_kernel.cuh) is the default; the dataflow kernel
+        // (flow_kernel.cuh) is available when X, E and KE of 16 chains fit shared memory and is selected with MAGI_K1=flow at
+        // create time (measured 8 % slower at 65 536 chains and 20 % slower at 4096 on FN n=201, profiles/README.md)
+        int KX = 0;
+        model_kx(h->model, KX);
+        h->flow_smem = flow_smem_bytes(h->D, h->K, KX, h->n, h->geom.HB, h->flow_RS0);
+        const char* force = getenv("MAGI_K1");
+        h->use_flow = h->flow_smem <= (size_t)prop.sharedMemPerBlockOptin && force && !strcmp(force, "flow");
+        if (force && !strcmp(force, "flow") && !h->use_flow) return fail(set_error(MAGI_ERR_UNSUPPORTED, "MAGI_K1=flow: the state of 16 chains does not fit shared memory"));
+        if (h->use_flow) {
+            const char* ord = getenv("MAGI_FLOW_LAG");      // development knob: wavefront order with this extra lag
+            std::vector<int> units = flow_unit_order(h->D, (h->geom.NT + 1) / 2, h->geom.HB, ord ? atoi(ord) : -1);
+            h->flow_units = (int)units.size();
+            if (cudaMalloc(&h->d_flow_units, sizeof(int) * units.size()) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc unit order failed"));
+            cudaMemcpy(h->d_flow_units, units.data(), sizeof(int) * units.size(), cudaMemcpyHostToDevice);
+        }
     }
     if (h->setup_mode != MAGI_SETUP_INJECT) {
         rc = run_device_setup(h);
@@ -181,7 +200,8 @@ static int ensure_scratch(magi_handle* h, int n_chains) {
 
 int refresh_fragtab(magi_handle* h, cudaStream_t st) {
     if (!h->frag_dirty || h->dense_mode) return MAGI_OK;
-    CK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], h->d_fragtab, h->n, h->b, h->D, st), "build_fragtab");
+    CK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], h->d_fragtab, h->n, h->b, h->D, h->use_flow,
+                            1.0 / h->beta[1], 1.0 / h->beta[0], st), "build_fragtab");      // 1/beta2 folded into C~, 1/beta1 into K~
     h->launches++;
     h->frag_dirty = false;
     return MAGI_OK;
@@ -194,6 +214,37 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     if (h->dense_mode) return eval_dense_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
     int rc = refresh_fragtab(h, st);
     if (rc) return rc;
+    if (h->use_flow) {
+        FlowArgs f;
+        f.n = h->n; f.P = h->P; f.n_chains = n_chains; f.NP = (h->geom.NT + 1) / 2; f.RS0 = h->flow_RS0; f.n_units = h->flow_units;
+        f.n_cblocks = (n_chains + 15) / 16;
+        f.sigma_is_fixed = h->sigma_is_fixed; f.sigma_invalid = h->sigma_invalid;
+        f.pitch = pitch; f.params = params_dev; f.ll = ll_dev; f.grad = grad_dev;
+        f.fragtab = h->d_fragtab; f.units = h->d_flow_units; f.yobs = h->d_yobs; f.nobs = h->d_nobs; f.sigma_init = h->d_sigma_init;
+        for (int i = 0; i < 3; ++i) { f.beta[i] = h->beta[i]; f.inv_beta[i] = 1.0 / h->beta[i]; }
+        const int grid = f.n_cblocks < h->sm_count ? f.n_cblocks : h->sm_count;
+        f.dbg = nullptr;
+        { static const char* e = getenv("MAGI_FLOW_STAGGER"); f.stagger = e ? atoi(e) : 0; }
+        static const bool dbg_flow = getenv("MAGI_DBG_CLOCKS") != nullptr;
+        long long* d_dbgf = nullptr;
+        if (dbg_flow) { cudaMalloc(&d_dbgf, sizeof(long long) * 16 * 16 * grid); cudaMemset(d_dbgf, 0, sizeof(long long) * 16 * 16 * grid); f.dbg = d_dbgf; }
+        CK(launch_flow_cfg(h->model, f, h->geom.HB, grid, h->flow_smem, st), "flow_logpost_kernel launch");
+        h->launches++;
+        if (dbg_flow) {
+            cudaStreamSynchronize(st);
+            std::vector<long long> v((size_t)16 * 16 * grid);
+            cudaMemcpy(v.data(), d_dbgf, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
+            double s[16] = {0};
+            for (int i = 0; i < 16 * grid; ++i) for (int j = 0; j < 16; ++j) s[j] += (double)v[(size_t)i * 16 + j];
+            const double nw = 16.0 * grid;
+            fprintf(stderr, "[magi dbg flow] grid=%d chain blocks=%d  avg cycles per warp: load wait=%.0f loop=%.0f (of which dependency waits=%.0f) loop tail=%.0f final=%.0f units=%.1f\n",
+                    grid, f.n_cblocks, s[0] / nw, s[1] / nw, s[2] / nw, s[3] / nw, s[4] / nw, s[5] / nw);
+            fprintf(stderr, "[magi dbg flow] timeline (-DMAGI_FLOW_TIMELINE) arrive=%.0f S1: product=%.0f pointwise=%.0f | S2: wait=%.0f product=%.0f pointwise=%.0f | S3: product1=%.0f wait=%.0f product2=%.0f pointwise=%.0f\n",
+                    s[6] / nw, s[7] / nw, s[8] / nw, s[9] / nw, s[10] / nw, s[11] / nw, s[12] / nw, s[13] / nw, s[14] / nw, s[15] / nw);
+            cudaFree(d_dbgf);
+        }
+        return MAGI_OK;
+    }
     select_block_shape(h, n_chains);
     rc = ensure_scratch(h, n_chains);
     if (rc) return rc;
@@ -257,8 +308,8 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
     { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
     const int per = nchunks > 0 ? ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32 : n_chains;
-    if (!h->dense_mode && h->tables_ready) select_block_shape(h, per);      // the shape every chunk will run with
-    if (n_chains >= 2 * chunk_min && !h->dense_mode && h->scratch_in_smem && h->tables_ready) {
+    if (!h->dense_mode && !h->use_flow && h->tables_ready) select_block_shape(h, per);      // the shape every chunk will run with
+    if (n_chains >= 2 * chunk_min && !h->dense_mode && (h->scratch_in_smem || h->use_flow) && h->tables_ready) {
         for (int i = 0; i < 3; ++i)
             if (!h->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
         rc = refresh_fragtab(h, h->stream);
@@ -362,6 +413,13 @@ extern "C" int magi_get_matrix(magi_handle* h, int dim, int which, double* out) 
     if (!h->d_dense[which]) return set_error(MAGI_ERR_NOT_READY, "get_matrix: dense matrices exist only after a device setup (setup_mode != INJECT)");
     const size_t nn = (size_t)h->n * h->n;
     CK(cudaMemcpy(out, h->d_dense[which] + (size_t)dim * nn, sizeof(double) * nn, cudaMemcpyDeviceToHost), "D2H dense matrix");
+    return MAGI_OK;
+}
+
+extern "C" int magi_setup_timing(const magi_handle* h, double* kernel_ms, double* alloc_ms) {
+    if (!h) return set_error(MAGI_ERR_INVALID_ARGUMENT, "setup_timing: null handle");
+    if (kernel_ms) *kernel_ms = h->setup_kernel_ms;
+    if (alloc_ms) *alloc_ms = h->setup_alloc_ms;
     return MAGI_OK;
 }
 

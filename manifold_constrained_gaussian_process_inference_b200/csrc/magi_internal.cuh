@@ -41,8 +41,18 @@ struct magi_handle {
     int smem_limit = 0, sm_count = 148;
     int G = 2, H = 1, DW = 1, scratch_in_smem = 1, gmax_cur = 4;
     size_t smem_bytes = 0;
+    // dataflow K1 (flow_kernel.cuh): chosen at create when the state of 16 chains fits shared memory
+    bool use_flow = false;
+    int flow_RS0 = 0, flow_units = 0;
+    size_t flow_smem = 0;
+    int* d_flow_units = nullptr;
     std::vector<int> repaired_c, repaired_k;
+    double setup_alloc_ms = 0.0, setup_kernel_ms = 0.0;   // device setup: host time in cudaMalloc / device time of K3-K6
     void* hmc = nullptr;     // on-device sampler state (hmc.cu)
+    // NCCL communicator of a multi-rank run (comm.cu): created from a unique id (owned) or attached by the host
+    void* nccl_comm = nullptr;
+    bool nccl_owned = false;
+    int nccl_rank = 0, nccl_world = 1;
 };
 
 namespace magi {
@@ -54,5 +64,9 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
 int eval_dense_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int run_device_setup(magi_handle* h);
 void hmc_free(magi_handle* h);
+void comm_free(magi_handle* h);
+int comm_allreduce_sum(magi_handle* h, double* buf, size_t n, cudaStream_t st);
+int comm_allgather(magi_handle* h, const double* send, double* recv, size_t n_per_rank, cudaStream_t st);
 cudaError_t launch_banded_cfg(int model, const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_flow_cfg(int model, const FlowArgs& a, int HB, int grid, size_t smem_bytes, cudaStream_t st);
 }  // namespace magi

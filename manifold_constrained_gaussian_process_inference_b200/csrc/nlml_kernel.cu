@@ -31,7 +31,12 @@ __global__ void __launch_bounds__(256) nlml_kernel(int kernel_id, int n, const d
         if (j > i) continue;
         double k;
         if (kernel_id == MAGI_KERNEL_RBF) { const double d = t[i] * s - t[j] * s; k = var * exp(-(d * d) / 2.0); }
-        else { const double r = fabs(t[i] * s - t[j] * s); k = var * ((1.0 + sqrt5 * r + 5.0 * r * r / 3.0) * exp(-sqrt5 * r)); }
+        else {
+            const double r = fabs(t[i] * s - t[j] * s);
+            if (kernel_id == MAGI_KERNEL_MATERN_NU12) k = var * exp(-r);                             // MaternKernel(nu), kernels.jl:109-118
+            else if (kernel_id == MAGI_KERNEL_MATERN_NU32) k = var * ((1.0 + sqrt(3.0) * r) * exp(-sqrt(3.0) * r));
+            else k = var * ((1.0 + sqrt5 * r + 5.0 * r * r / 3.0) * exp(-sqrt5 * r));
+        }
         A[idx] = k + (i == j ? diag_add : 0.0);                                                  // :128
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = y[i];
@@ -100,8 +105,8 @@ extern "C" int magi_gp_nlml_batched(int kernel_id, int n, const double* t, const
     cudaMemcpy(d_t, t, sizeof(double) * n, cudaMemcpyHostToDevice);
     cudaMemcpy(d_y, y, sizeof(double) * n, cudaMemcpyHostToDevice);
     cudaMemcpy(d_lp, log_params, sizeof(double) * 3 * n_cand, cudaMemcpyHostToDevice);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(nlml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64); attr_set = true; }
+    static PerDeviceOnce once;
+    if (once.need()) cudaFuncSetAttribute(nlml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64);
     nlml_kernel<<<n_cand, 256, use_smem ? smem_need : 0>>>(kernel_id, n, d_t, d_y, jitter, d_lp, d_out, d_work, use_smem);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * n_cand, cudaMemcpyDeviceToHost);

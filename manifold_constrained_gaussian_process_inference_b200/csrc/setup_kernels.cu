@@ -5,6 +5,7 @@
 //       (:296, :302-307, :318) -- or, setup_mode "stable", W = L^-1 C'^T, K = C'' - W^T W + eI, m = (L^-T W)^T
 //   K6  band extraction into diagonal-major tables (:358-360, mat2band :70-74)
 // All matrices are column-major n x n, batched over the D dimensions (batch stride n*n).
+#include <chrono>
 #include <cmath>
 #include <cfloat>
 #include "magi_internal.cuh"
@@ -46,6 +47,12 @@ __global__ void cov_build_kernel(int kernel_id, int complexity, const double* __
                     cpp = var * (term1 + term2);                                                  // :118
                 }
             }
+        } else if (kernel_id == MAGI_KERNEL_MATERN_NU12 || kernel_id == MAGI_KERNEL_MATERN_NU32 || kernel_id == MAGI_KERNEL_MATERN_NU52) {
+            // MaternKernel(nu) (kernels.jl:109-118) in closed form; no analytic derivatives in the reference (:278-280)
+            const double r = fabs(ti * s - tj * s);
+            if (kernel_id == MAGI_KERNEL_MATERN_NU12) c = var * exp(-r);
+            else if (kernel_id == MAGI_KERNEL_MATERN_NU32) c = var * ((1.0 + sqrt(3.0) * r) * exp(-sqrt(3.0) * r));
+            else c = var * ((1.0 + sqrt5 * r + 5.0 * r * r / 3.0) * exp(-sqrt5 * r));
         } else {
             const double dd = ti * s - tj * s;
             c = var * exp(-(dd * dd) / 2.0);
@@ -223,6 +230,7 @@ struct SetupCtx {
     cudaStream_t st;
     long long launches = 0;
     std::vector<int> rep_c, rep_k;
+    double alloc_ms = 0.0, kernel_ms = 0.0;   // host time spent in cudaMalloc / device time from the covariance build to the band tables
 };
 
 static dim3 ew_grid(size_t count, int D) {
@@ -345,18 +353,25 @@ int gp_setup_device(SetupCtx& c) {
     auto cleanup = [&]() { cudaFree(L); cudaFree(X); cudaFree(T); cudaFree(d_tinv); cudaFree(d_stat); cudaFree(d_rep); };
 #define SETUP_TRY(expr) do { int rc__ = (expr); if (rc__ != MAGI_OK) { cleanup(); return rc__; } } while (0)
 #define SETUP_CUDA(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return cuda_error(e__, what); } } while (0)
+    const auto t_alloc0 = std::chrono::steady_clock::now();
     SETUP_CUDA(cudaMalloc(&L, sizeof(double) * nn * D), "cudaMalloc setup L");
     SETUP_CUDA(cudaMalloc(&X, sizeof(double) * nn * D), "cudaMalloc setup X");
     SETUP_CUDA(cudaMalloc(&T, sizeof(double) * nn * D), "cudaMalloc setup T");
     SETUP_CUDA(cudaMalloc(&d_tinv, sizeof(double) * (size_t)D * nblk * NBMAX * NBMAX), "cudaMalloc tinv");
     SETUP_CUDA(cudaMalloc(&d_stat, sizeof(double) * 2 * D), "cudaMalloc stat");
     SETUP_CUDA(cudaMalloc(&d_rep, sizeof(int) * D), "cudaMalloc rep");
+    c.alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc0).count();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, c.st);
     SETUP_CUDA(cudaMemsetAsync(T, 0, sizeof(double) * nn * D, c.st), "memset T");
     const dim3 eg = ew_grid(nn, D);
     const bool want_deriv = c.complexity >= 2 && (c.kernel_id == MAGI_KERNEL_MATERN52 || c.kernel_id == MAGI_KERNEL_RBF);
     cov_build_kernel<<<eg, 256, 0, c.st>>>(c.kernel_id, want_deriv ? 2 : 0, c.d_tvec, c.d_phi, n, C, Cp, Cpp); c.launches++;
     SETUP_CUDA(cudaGetLastError(), "cov_build_kernel");
-    // derivatives "all zero" test of the reference (:299): any dimension with all-zero C' or C'' takes the fallback
+    // derivatives "all zero" test of the reference (:299), decided PER DIMENSION like the reference's per-GPCov call: a
+    // dimension with all-zero C' or C'' (n = 1; a lengthscale so small that every off-diagonal entry underflows) takes the
+    // fallback, the others the full path
     std::vector<double> st(2 * D, 0.0);
     SETUP_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(double) * 2 * D, c.st), "memset stats");
     const int abs_chunks = (int)std::min<size_t>(64, ((size_t)n * n + 65535) / 65536);
@@ -364,8 +379,9 @@ int gp_setup_device(SetupCtx& c) {
     absmax_kernel<<<dim3(D, abs_chunks), 256, 0, c.st>>>(Cpp, n, 0, d_stat + D); c.launches++;
     SETUP_CUDA(cudaMemcpyAsync(st.data(), d_stat, sizeof(double) * 2 * D, cudaMemcpyDeviceToHost, c.st), "D2H stats");
     SETUP_CUDA(cudaStreamSynchronize(c.st), "sync");
-    bool deriv = want_deriv;
-    for (int d = 0; d < D; ++d) if (!(st[d] > 0.0) || !(st[D + d] > 0.0)) deriv = false;
+    std::vector<char> deriv_d(D, 0);
+    bool deriv = false;
+    for (int d = 0; d < D; ++d) { deriv_d[d] = want_deriv && st[d] > 0.0 && st[D + d] > 0.0; deriv = deriv || deriv_d[d]; }
     // C + eI -> L ; X = inv(L) ; Cinv
     add_jitter_sym_kernel<<<eg, 256, 0, c.st>>>(C, L, n, c.jitter, 1); c.launches++;
     SETUP_TRY(chol_and_inverse(c, L, X, T, d_tinv, d_stat, d_rep, NB, nblk));
@@ -395,6 +411,17 @@ int gp_setup_device(SetupCtx& c) {
         c.rep_k.assign(D, 0);
         SETUP_CUDA(cudaMemcpyAsync(c.rep_k.data(), d_rep, sizeof(int) * D, cudaMemcpyDeviceToHost, c.st), "D2H repaired");
         SETUP_TRY(inverse_from_factor(c, X, Kinv));
+        SETUP_CUDA(cudaStreamSynchronize(c.st), "sync");
+        for (int d = 0; d < D; ++d) {
+            if (deriv_d[d]) continue;                 // this dimension alone takes the fallback (:319-331)
+            const dim3 e1 = ew_grid(nn, 1);
+            SETUP_CUDA(cudaMemsetAsync(Cp + d * nn, 0, sizeof(double) * nn, c.st), "memset");
+            SETUP_CUDA(cudaMemsetAsync(Cpp + d * nn, 0, sizeof(double) * nn, c.st), "memset");
+            SETUP_CUDA(cudaMemsetAsync(mphi + d * nn, 0, sizeof(double) * nn, c.st), "memset");
+            set_diag_kernel<<<e1, 256, 0, c.st>>>(Kphi + d * nn, n, c.jitter); c.launches++;
+            set_diag_kernel<<<e1, 256, 0, c.st>>>(Kinv + d * nn, n, 1.0 / c.jitter); c.launches++;
+            c.rep_k[d] = 0;
+        }
     } else {
         // zero-derivative fallback (:278-280, :319-331): C' = C'' = m = 0, K = eI, Kinv = I/e
         SETUP_CUDA(cudaMemsetAsync(Cp, 0, sizeof(double) * nn * D, c.st), "memset");
@@ -409,7 +436,10 @@ int gp_setup_device(SetupCtx& c) {
     band_extract_kernel<<<bg, 256, 0, c.st>>>(mphi, c.band[1], n, c.b); c.launches++;
     band_extract_kernel<<<bg, 256, 0, c.st>>>(Kinv, c.band[2], n, c.b); c.launches++;
     SETUP_CUDA(cudaGetLastError(), "band_extract_kernel");
+    cudaEventRecord(ev1, c.st);
     SETUP_CUDA(cudaStreamSynchronize(c.st), "setup sync");
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) c.kernel_ms = ms; }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     cleanup();
     return MAGI_OK;
 }
@@ -417,10 +447,12 @@ int gp_setup_device(SetupCtx& c) {
 // setup for a whole handle (all D dimensions batched)
 int run_device_setup(magi_handle* h) {
     const size_t nn = (size_t)h->n * h->n;
+    const auto t_alloc0 = std::chrono::steady_clock::now();
     for (int i = 0; i < 7; ++i) {
         cudaError_t e = cudaMalloc(&h->d_dense[i], sizeof(double) * nn * h->D);
         if (e != cudaSuccess) return cuda_error(e, "cudaMalloc dense GP matrices");
     }
+    const double alloc_dense_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc0).count();
     double *d_t = nullptr, *d_phi = nullptr;
     if (cudaMalloc(&d_t, sizeof(double) * h->n) != cudaSuccess || cudaMalloc(&d_phi, sizeof(double) * 2 * h->D) != cudaSuccess) {
         cudaFree(d_t); cudaFree(d_phi);
@@ -437,6 +469,7 @@ int run_device_setup(magi_handle* h) {
     cudaFree(d_t); cudaFree(d_phi);
     h->launches += c.launches;
     if (rc != MAGI_OK) return rc;
+    h->setup_alloc_ms = alloc_dense_ms + c.alloc_ms; h->setup_kernel_ms = c.kernel_ms;
     h->repaired_c = c.rep_c; h->repaired_k = c.rep_k;
     std::fill(h->band_set.begin(), h->band_set.end(), 1);
     h->tables_ready = true; h->frag_dirty = true; h->dense_band_dirty = true;
@@ -455,6 +488,7 @@ extern "C" int magi_gp_covariances(int kernel_id, const double* phi, const doubl
                                    double* mphiBand, double* KinvBand, int* repaired /* [2] or NULL */) {
     if (!phi || !tvec || n < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_gp_covariances: bad argument");
     if (setup_mode != MAGI_SETUP_REFERENCE_ORDER && setup_mode != MAGI_SETUP_STABLE) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_gp_covariances: bad setup_mode");
+    if (kernel_id < MAGI_KERNEL_MATERN52 || kernel_id > MAGI_KERNEL_MATERN_NU52) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_gp_covariances: unknown kernel_id");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(MAGI_ERR_CUDA, "magi_gp_covariances: no CUDA device available (no CPU fallback)");
     if (cudaSetDevice(device) != cudaSuccess) return set_error(MAGI_ERR_CUDA, "cudaSetDevice failed");

@@ -1,6 +1,9 @@
 """Multi-GPU plumbing: chains shard across ranks with NO collective on the hot path (every rank rebuilds the identical
 GP tables locally); one all-gather of the retained scalar draws (θ, σ, lp) at the end of a run feeds R-hat / ESS
-(SURVEY.md section 8(e)).  torch.distributed is the transport: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+(SURVEY.md section 8(e)).  On GPUs both exchange steps (the warm-up's pooled window statistics and the final all-gather) run
+inside libmagi_b200 with NCCL on the sampler's stream (``init_device_comm`` / ``allgather_draws_device``; csrc/comm.cu);
+``torch.distributed`` only carries the 128-byte NCCL unique id between the ranks.  ``allgather_draws`` is the
+transport-agnostic host path (gloo in the CPU tests)."""
 from __future__ import annotations
 
 import numpy as np
@@ -24,9 +27,8 @@ def allgather_draws(local_draws, group=None):
         return local_draws
     world = dist.get_world_size(group)
     n_iter, n_local, n_cols = local_draws.shape
-    counts = [torch.zeros(1, dtype=torch.int64, device=local_draws.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=local_draws.device), group=group)
-    counts = [int(c.item()) for c in counts]
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n_local), group=group)          # host-side exchange of the shard sizes: no device sync
     nmax = max(counts)
     pad = local_draws
     if n_local < nmax:
@@ -78,3 +80,39 @@ def make_window_allreduce(target, group=None):
             traceback.print_exc()
             return 1
     return _lib.ALLREDUCE_FN(_cb)
+
+
+def init_device_comm(target, group=None):
+    """Creates the NCCL communicator libmagi_b200 uses for ``target``'s sampler (collective over ``group``): rank 0 draws
+    the unique id, torch.distributed broadcasts its 128 bytes, every rank calls ``magi_comm_init``; one small all-reduce /
+    all-gather then warms the communicator so that the first real collective is not charged its set-up."""
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    L = _lib.lib()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.magi_nccl_unique_id(buf))
+    box = [buf.raw]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    _lib.check(L.magi_comm_init(target._h, box[0], rank, world))
+    _lib.check(L.magi_comm_warmup(target._h, None))
+
+
+def allgather_draws_device(target, stream: int = 0):
+    """All-gather of the on-device draw store over the library's communicator (``init_device_comm``): returns a CUDA tensor
+    (n_iter, n_chains_total, n_cols) with chains in global order.  Every rank must hold equally many chains."""
+    import ctypes
+    import torch
+    from . import _lib
+    from .samplers import hmc_draws_device_view
+    L = _lib.lib()
+    _, ns, nc, ncol = hmc_draws_device_view(target)
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    out = torch.empty((world, ns, nc, ncol), dtype=torch.float64, device="cuda:%d" % target.device)
+    _lib.check(L.magi_hmc_allgather_draws(target._h, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)))
+    return out.permute(1, 0, 2, 3).reshape(ns, world * nc, ncol)

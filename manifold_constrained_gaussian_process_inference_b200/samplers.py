@@ -16,14 +16,16 @@ from .target import MagiTarget
 def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n_adapts: int = 1000,
                     target_accept_ratio: float = 0.8, initial_step_size: float = 0.1, n_leapfrog: int = 20,
                     seed: int = 0, chain_id_offset: int = 0, keep_on_device: bool = False,
-                    n_chains_total: int | None = None, window_allreduce=None):
+                    n_chains_total: int | None = None, window_allreduce=None, stream: int = 0):
     """Argument meaning follows ``run_nuts_sampler``: ``n_samples`` is the TOTAL number of iterations including the
     ``n_adapts`` warm-up iterations, which are dropped (``drop_warmup=true``).  ``initial_params`` is (n_chains, P).
 
-    Multi-rank runs (chains sharded over GPUs): pass the global chain count as ``n_chains_total`` and
-    ``window_allreduce = distributed.make_window_allreduce(target)``; the pooled metric of the warm-up is then a statistic
-    of ALL ranks' chains, and the run is bit-identical to a one-rank run over the same global chains (shards aligned to
-    ``n_chains_total / 64`` chains).
+    Multi-rank runs (chains sharded over GPUs): call ``distributed.init_device_comm(target)`` first and pass the global chain
+    count as ``n_chains_total``; the pooled metric of the warm-up is then a statistic of ALL ranks' chains (one ncclAllReduce
+    per adaptation window inside the library), and the run is bit-identical to a one-rank run over the same global chains
+    (shards aligned to ``n_chains_total / 64`` chains).  ``window_allreduce`` (``distributed.make_window_allreduce``) is the
+    host-callback alternative for transports other than NCCL.  ``stream``: CUDA stream handle the sampler runs on (0: the
+    handle's own stream).
 
     Returns ``(chain, stats)``: ``chain`` is an array (n_kept, n_chains, k + D + 1) of (θ, σ, lp) draws and ``stats`` a
     dict with per-chain acceptance rate, step size, divergences, posterior mean of X, the adapted inverse metric and
@@ -42,11 +44,11 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
         target._window_allreduce = cb                      # keep the ctypes callback alive as long as the handle
         _lib.check(L.magi_hmc_set_global(h, ctypes.c_longlong(int(n_chains_total if n_chains_total is not None else nc + chain_id_offset)), cb, None))
     if n_adapts > 0:
-        _lib.check(L.magi_hmc_run(h, int(n_adapts), int(n_leapfrog), 1, float(target_accept_ratio), 0, None))
+        _lib.check(L.magi_hmc_run(h, int(n_adapts), int(n_leapfrog), 1, float(target_accept_ratio), 0, ctypes.c_void_p(stream) if stream else None))
     _lib.check(L.magi_hmc_reset_stats(h))
     n_keep = int(n_samples) - int(n_adapts)
     if n_keep > 0:
-        _lib.check(L.magi_hmc_run(h, n_keep, int(n_leapfrog), 0, float(target_accept_ratio), 1, None))
+        _lib.check(L.magi_hmc_run(h, n_keep, int(n_leapfrog), 0, float(target_accept_ratio), 1, ctypes.c_void_p(stream) if stream else None))
     ncols = target.n_params_ode + target.n_dims + 1
     chain = None
     if not keep_on_device:

@@ -85,6 +85,10 @@ def solve_magi(y_obs, t_obs, ode_system: OdeSystem, config=None, initial_params=
     phi = get("phi", None)
     sigma = get("sigma", None)
     sigma_is_fixed = (sigma is not None) and (phi is not None)               # :224
+    if sigma is not None and phi is None:                                   # :233-236: sigma without phi is discarded and re-initialised
+        import warnings
+        warnings.warn("Sigma provided but Phi not provided. Sigma will be treated as unknown and re-initialized.")
+        sigma = None
     device = int(get("device", 0))
     sigma_est = None
     if phi is None or sigma is None:                                        # :254-330: Option A, estimate per dimension

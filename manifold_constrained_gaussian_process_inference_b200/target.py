@@ -128,6 +128,12 @@ class MagiTarget:
         _lib.check(self._L.magi_setup_status(self._h, dim, ctypes.byref(a), ctypes.byref(b)))
         return int(a.value), int(b.value)
 
+    def setup_timing(self):
+        """(kernel_ms, alloc_ms) of the device GP setup inside ``magi_create``: device time of K3-K6, host time in cudaMalloc."""
+        k, a = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self._L.magi_setup_timing(self._h, ctypes.byref(k), ctypes.byref(a)))
+        return float(k.value), float(a.value)
+
     # ---- LogDensityProblems interface ----
     def dimension(self) -> int:
         return int(self._L.magi_dimension(self._h))

@@ -43,7 +43,8 @@ import numpy as np
 
 MATERN52 = 0
 RBF = 1
-KERNEL_IDS = {"matern52": MATERN52, "rbf": RBF}
+MATERN_NU12, MATERN_NU32, MATERN_NU52 = 2, 3, 4      # MaternKernel(ν) of src/kernels.jl:109-118 (no time derivatives in the reference)
+KERNEL_IDS = {"matern52": MATERN52, "rbf": RBF, "matern_nu12": MATERN_NU12, "matern_nu32": MATERN_NU32, "matern_nu52": MATERN_NU52}
 
 
 def kernel_matrix(kernel: int, tvec, variance, lengthscale):
@@ -56,10 +57,16 @@ def kernel_matrix(kernel: int, tvec, variance, lengthscale):
     s = dt(1.0) / dt(lengthscale)
     ts = t * s
     diff = ts[:, None] - ts[None, :]
-    if kernel == MATERN52:
+    if kernel in (MATERN52, MATERN_NU52):
         d = np.abs(diff)
         sqrt5 = np.sqrt(dt(5.0))
         base = (dt(1.0) + sqrt5 * d + dt(5.0) * d * d / dt(3.0)) * np.exp(-sqrt5 * d)
+    elif kernel == MATERN_NU32:
+        d = np.abs(diff)
+        sqrt3 = np.sqrt(dt(3.0))
+        base = (dt(1.0) + sqrt3 * d) * np.exp(-sqrt3 * d)
+    elif kernel == MATERN_NU12:
+        base = np.exp(-np.abs(diff))
     elif kernel == RBF:
         base = np.exp(-(diff * diff) / dt(2.0))
     else:
@@ -287,7 +294,7 @@ def calculate_gp_covariances(kernel: int, phi, tvec, bandsize: int, complexity: 
     g = GPCov(phi=np.asarray(phi, dtype=dtype), tvec=t, kernel=kernel, bandsize=bandsize, setup_mode=setup_mode)
     eps = dt(jitter)
     I = np.eye(n, dtype=dtype)
-    g.C = kernel_matrix(kernel if kernel in (MATERN52, RBF) else MATERN52, t, variance, lengthscale)
+    g.C = kernel_matrix(kernel, t, variance, lengthscale)
     Cj = g.C + eps * I                                           # :257
     derivatives = False
     g.Cprime = np.zeros((n, n), dtype=dtype)

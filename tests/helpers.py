@@ -106,3 +106,13 @@ def assert_parity(ll, grad, ll_ref, grad_ref, what=""):
         err = np.where(ok, np.abs(grad - grad_ref) / np.where(scale > 0, scale, 1.0), 0.0)
         assert err.max() <= GRAD_RTOL, "%s: gradient error %.3e > %.1e" % (what, err.max(), GRAD_RTOL)
     return float(rel.max()) if rel.size else 0.0
+
+
+def fn_n3_golden():
+    """(ll, grad[11], rtol): the FN N=3 case of test/test_likelihoods.jl:18-59 in long double (tests/golden/reference_known_answers.json);
+    the single constant both the oracle pins and the GPU parity tests compare with."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")) as f:
+        g = json.load(f)["restated_fn_n3_values"]
+    return float(g["ll"]), np.array(g["grad"]), float(g["rtol"])

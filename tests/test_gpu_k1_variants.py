@@ -1,0 +1,82 @@
+"""Both K1 kernels against the oracle and against each other.  `magi_create` picks the dataflow kernel (flow_kernel.cuh) when
+the state of 16 chains fits shared memory and the windowed kernel (banded_kernel.cuh) otherwise; MAGI_K1 forces one at create
+time (development knob), so every shape below runs through both code paths on identical inputs.
+Tolerance: tests/helpers.py (1e-10 relative)."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _target(pkg, prob, monkeypatch, variant):
+    monkeypatch.setenv("MAGI_K1", variant)
+    return H.cuda_target(pkg, prob)
+
+
+@pytest.mark.parametrize("model,n,b,nc,kw", [
+    ("fn", 201, 20, 40, {}),                                 # BASELINE config 2 shape: 3 chain blocks, the last one partial
+    ("fn", 201, 20, 16, {"beta": (2.0, 3.0, 5.0)}),
+    ("fn", 41, 6, 37, {}),
+    ("fn", 16, 0, 8, {}),                                    # diagonal band: NCH = 2, no halo pairs
+    ("fn", 9, 1, 3, {}),
+    ("fn", 1, 0, 2, {"obs_every": 1}),
+    ("fn", 50, 16, 12, {"sigma_fixed": True}),
+    ("fn", 64, 32, 17, {}),                                  # widest band of the DMMA tiling (HB = 8)
+    ("fn", 120, 9, 33, {"T": 12.0}),
+    ("lv", 81, 20, 10, {"T": 4.0}),
+    ("hes1", 33, 5, 13, {}),                                 # D = 3
+    ("hes1", 64, 12, 20, {}),
+])
+def test_flow_and_windowed_kernels_match_the_oracle(pkg, monkeypatch, model, n, b, nc, kw):
+    prob = H.make_problem(model=model, n=n, b=b, n_chains=nc, seed=7 * n + b, **kw)
+    ll_ref, g_ref = H.oracle_batched(prob)
+    out = {}
+    for variant in ("flow", "windowed"):
+        tg = _target(pkg, prob, monkeypatch, variant)
+        ll, g = tg.logdensity_and_gradient_batched(prob["params"])
+        H.assert_parity(ll, g, ll_ref, g_ref, "%s %s n=%d b=%d" % (variant, model, n, b))
+        ll2, _ = tg.logdensity_and_gradient_batched(prob["params"], want_grad=False)
+        assert np.array_equal(ll, ll2)
+        out[variant] = (ll, g)
+        tg.close()
+    H.assert_parity(out["flow"][0], out["flow"][1], out["windowed"][0], out["windowed"][1], "flow vs windowed")
+
+
+def test_flow_kernel_is_persistent_and_deterministic(pkg, monkeypatch):
+    """More chain blocks than SMs (every block of the persistent grid handles several; the mbarrier phases alternate), a
+    partial last block, and bit-identical results from two launches (units are drawn dynamically, sums are not)."""
+    nc = 148 * 16 * 2 + 16 * 5 + 3
+    base = H.make_problem(model="fn", n=201, b=20, n_chains=8, seed=11, T=20.0, obs_every=5)
+    rng = np.random.default_rng(3)
+    params = np.repeat(base["params"], (nc + 7) // 8, axis=0)[:nc] + 1e-3 * rng.normal(size=(nc, base["params"].shape[1]))
+    tg = _target(pkg, base, monkeypatch, "flow")
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    ll_b, g_b = tg.logdensity_and_gradient_batched(params)
+    assert np.array_equal(ll, ll_b) and np.array_equal(g, g_b)
+    idx = np.unique(np.concatenate([[0, 1, 15, 16, nc // 2, nc - 4, nc - 3, nc - 2, nc - 1], rng.integers(0, nc, size=9)]))
+    ll_ref, g_ref = H.oracle_batched(base, params[idx])
+    H.assert_parity(ll[idx], g[idx], ll_ref, g_ref, "flow kernel, persistent grid")
+    # a chain gives the same bits wherever it sits in the batch
+    sub = np.concatenate([idx, np.arange(200, 230)])
+    ll2, g2 = tg.logdensity_and_gradient_batched(params[sub])
+    assert np.array_equal(ll[sub], ll2) and np.array_equal(g[sub], g2)
+
+
+def test_flow_kernel_guards_are_per_chain(pkg, monkeypatch):
+    """interface.jl:222-226, 260-264 per chain: a poisoned chain returns (-Inf, zeros) and leaves its neighbours alone."""
+    prob = H.make_problem(model="fn", n=41, b=6, n_chains=20, seed=5)
+    tg = _target(pkg, prob, monkeypatch, "flow")
+    ll0, g0 = tg.logdensity_and_gradient_batched(prob["params"])
+    bad = prob["params"].copy()
+    bad[3, 7] = np.nan                   # a state value
+    bad[9, 2 * 41 + 2] = np.inf          # theta_3
+    bad[17, 2 * 41 + 3] = np.nan         # log sigma_1
+    ll, g = tg.logdensity_and_gradient_batched(bad)
+    for c in (3, 9, 17):
+        assert ll[c] == -np.inf and np.all(g[c] == 0.0)
+    keep = np.setdiff1d(np.arange(20), [3, 9, 17])
+    assert np.array_equal(ll[keep], ll0[keep]) and np.array_equal(g[keep], g0[keep])
+    ll_ref, g_ref = H.oracle_batched(prob, bad)
+    H.assert_parity(ll, g, ll_ref, g_ref, "guards")

@@ -140,3 +140,39 @@ def test_create_with_device_setup_matches_injected_tables(pkg):
     ll_ref, g_ref = H.oracle_batched(prob)
     rel = np.abs(l1 - ll_ref) / np.abs(ll_ref)
     assert rel.max() < 1e-6
+
+
+@pytest.mark.parametrize("nu,closed", [(0.5, lambda r: np.exp(-r)), (1.5, lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r)),
+                                       (2.5, lambda r: (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r))])
+def test_general_matern_kernel_takes_the_zero_derivative_fallback(pkg, nu, closed):
+    """src/gaussian_process.jl:278-280: a base kernel other than Matern52Kernel / SqExponentialKernel (here MaternKernel(nu),
+    src/kernels.jl:109-118) gets its C, a warning, and C' = C'' = m = 0, K = eI, Kinv = I/e (:319-331) -- not an error."""
+    t = np.arange(0.0, 1.0 + 1e-9, 0.25)
+    n, var, ell, eps = len(t), 1.3, 0.6, 1e-5
+    g = pkg.GPCov()
+    pkg.calculate_gp_covariances(g, pkg.create_general_matern_kernel(var, ell, nu), [var, ell], t, 2, complexity=2, jitter=eps)
+    r = np.abs(t[:, None] - t[None, :]) / ell
+    assert np.allclose(g.C, var * closed(r), rtol=1e-13, atol=0)
+    assert not g.Cprime.any() and not g.Cdoubleprime.any() and not g.mphi.any()
+    assert np.allclose(g.Kphi, eps * np.eye(n), atol=1e-18) and np.allclose(g.Kinv, np.eye(n) / eps, rtol=1e-9)
+    assert np.max(np.abs((g.C + eps * np.eye(n)) @ g.Cinv - np.eye(n))) < 1e-6
+    o = mo.calculate_gp_covariances(mo.KERNEL_IDS[g.kernel.kind], [var, ell], t, 2, complexity=2, jitter=eps)
+    assert np.max(np.abs(g.Cinv - o.Cinv)) <= 1e-9 * np.abs(o.Cinv).max() and np.array_equal(g.mphiBand, o.mphiBand)
+
+
+def test_zero_derivative_fallback_is_decided_per_dimension(pkg):
+    """src/gaussian_process.jl:299 runs once per GPCov: a dimension whose C' is all zero (here: a lengthscale so short that
+    every off-diagonal entry underflows) takes the fallback alone; the other dimension gets the full tables."""
+    prob = H.make_problem(model="fn", n=21, T=10.0, b=5, n_chains=4, seed=9)
+    phi = np.array([[2.0, 1.0], [1.5, 1e-4]])          # row 0 variances, row 1 lengthscales: dimension 1 underflows
+    tg = pkg.MagiTarget.from_config(prob["Y"], prob["tvec"], phi, pkg.fn_system(), prob["sigma_init"], bandsize=5, jitter=1e-6)
+    g0 = pkg.GPCov()
+    pkg.calculate_gp_covariances(g0, pkg.create_matern52_kernel(2.0, 1.5), [2.0, 1.5], prob["tvec"], 5, complexity=2, jitter=1e-6)
+    for name in ("CinvBand", "mphiBand", "KinvBand"):
+        assert np.array_equal(tg.get_band_table(0, name), getattr(g0, name)), name
+    assert np.any(tg.get_matrix(0, "mphi") != 0.0)
+    n = 21
+    assert not tg.get_matrix(1, "Cprime").any() and not tg.get_matrix(1, "mphi").any()
+    assert np.allclose(tg.get_matrix(1, "Kinv"), np.eye(n) / 1e-6, rtol=1e-9) and np.allclose(tg.get_matrix(1, "Kphi"), 1e-6 * np.eye(n), atol=1e-20)
+    ll, g = tg.logdensity_and_gradient_batched(prob["params"])
+    assert np.all(np.isfinite(ll)) and np.all(np.isfinite(g))

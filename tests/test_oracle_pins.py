@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import magi_oracle as mo
+from tests import helpers as H
 
 
 def _fd_grad(f, v, rel=1e-5):
@@ -33,9 +34,10 @@ def test_fn_gradient_matches_finite_differences():
     fd = _fd_grad(f, np.concatenate([X.reshape(-1, order="F"), th]))
     assert np.allclose(g[:9], fd, rtol=1e-3, atol=1e-4)
     assert np.max(np.abs(g[:9] - fd) / np.maximum(1, np.abs(fd))) < 1e-8
-    # restated values cross-checked against SURVEY.md section 8(c) (not reference-verified)
-    assert abs(ll - (-1898.99907936529)) < 1e-6
-    assert np.allclose(g[9:], [-27.0, -19.585185185185], rtol=1e-10)
+    # frozen long-double evaluation of the restatement (tests/golden/reference_known_answers.json; not reference-verified)
+    ll_gold, g_gold, rtol = H.fn_n3_golden()
+    assert abs(ll - ll_gold) <= rtol * abs(ll_gold)
+    assert np.max(np.abs(g - g_gold) / np.maximum(1.0, np.abs(g_gold))) <= rtol
     # sigma gradient against FD as well (pinned only by the formula, likelihoods.jl:229-246)
     fs = lambda s: mo.log_likelihood_and_gradient_banded(X, th, s, Y, covs, fn)[0]
     assert np.allclose(g[9:], _fd_grad(fs, sig.copy(), rel=1e-6), rtol=1e-6)
@@ -120,6 +122,16 @@ def test_gp_fallbacks_and_edge_cases():
     assert g0.CinvBand.shape == (1, 5) and np.allclose(g0.CinvBand[0], np.diag(g0.Cinv))
     gf = mo.calculate_gp_covariances(mo.RBF, [2.5, 0.3], np.linspace(0, 1, 5), 4, complexity=2, jitter=1e-6)
     assert np.array_equal(mo.band_from_storage(gf.KinvBand, 4), gf.Kinv)
+
+
+def test_general_matern_kernels_take_the_fallback():
+    """src/kernels.jl:109-118 + src/gaussian_process.jl:278-280: MaternKernel(nu) has no analytic derivatives in the reference."""
+    t = np.arange(0.0, 1.0 + 1e-9, 0.25); n = len(t)
+    for kid, f in ((mo.MATERN_NU12, lambda r: np.exp(-r)), (mo.MATERN_NU32, lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r)),
+                   (mo.MATERN_NU52, lambda r: (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r))):
+        g = mo.calculate_gp_covariances(kid, [1.3, 0.6], t, 2, complexity=2, jitter=1e-5)
+        assert np.allclose(g.C, 1.3 * f(np.abs(t[:, None] - t[None, :]) / 0.6), rtol=1e-14)
+        assert not g.Cprime.any() and not g.mphi.any() and np.allclose(g.Kinv, np.eye(n) / 1e-5, rtol=1e-9)
 
 
 def test_mat2band_rule():

@@ -1,0 +1,20 @@
+"""Development aid: builds lib/libmagi_<name>.so = the objects of the fast build with flow_inst_0.cu (FN) recompiled with
+extra -D flags, so that kernel variants can be measured side by side in ONE gpurun call (MAGI_LIB_NAME selects the library).
+usage: python tools/build_variant.py <name> [-DFOO=1 ...]"""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "manifold_constrained_gaussian_process_inference_b200")
+sys.path.insert(0, ROOT)
+from manifold_constrained_gaussian_process_inference_b200 import build as B
+
+name, defs = sys.argv[1], sys.argv[2:]
+B.build(fast=True)                                           # refreshes build_fast/*.o (and the default fast .so)
+objdir = os.path.join(PKG, "build_fast")
+vdir = os.path.join(PKG, "build_var", name)
+os.makedirs(vdir, exist_ok=True)
+obj = os.path.join(vdir, "flow_inst_0.o")
+subprocess.check_call([B.NVCC] + B.FLAGS + ["-DMAGI_FAST_BUILD"] + defs + ["-c", os.path.join(B.CSRC, "flow_inst_0.cu"), "-o", obj])
+others = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir)) if f.endswith(".o") and f != "flow_inst_0.o"]
+lib = os.path.join(PKG, "lib", "libmagi_%s.so" % name)
+subprocess.check_call([B.NVCC, "-shared", "-o", lib] + others + [obj, "-gencode", "arch=compute_100a,code=sm_100a"])
+print(lib)
