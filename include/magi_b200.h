@@ -172,6 +172,11 @@ int magi_hmc_reset_stats(magi_handle* h);
 int magi_hmc_get_state(magi_handle* h, double* params /* P x n_chains or NULL */, double* ll /* n_chains or NULL */);
 /* draws: [n_stored][n_chains][k + D + 1] = (theta, sigma, lp) like solve_magi's theta / sigma / lp (src/MagiJl.jl:633-771) */
 int magi_hmc_get_draws(magi_handle* h, double* out, long long max_iters, long long* n_stored);
+/* X draws: vec(X) (n*D doubles, time fastest) of the first n_chains_x chains at every thin-th kept iteration -- x_sampled of
+ * solve_magi's result (src/MagiJl.jl:633-771).  magi_hmc_store_x after magi_hmc_init, before the kept iterations;
+ * magi_hmc_get_x_draws fills out[n_stored][n_chains_x][n*D]. */
+int magi_hmc_store_x(magi_handle* h, int n_chains_x, int thin);
+int magi_hmc_get_x_draws(magi_handle* h, double* out, long long max_draws, long long* n_stored, int* n_chains_x);
 int magi_hmc_draws_dev(magi_handle* h, void** ptr_dev, long long* n_stored, int* n_chains, int* n_cols);
 int magi_hmc_get_stats(magi_handle* h, double* accept_rate, double* step_size, int* n_divergent, double* xmean /* nD x n_chains */,
                        double* minv /* P */);

@@ -7,7 +7,7 @@ from . import _lib
 from .kernels import Kernel, create_general_matern_kernel, create_matern52_kernel, create_rbf_kernel
 from .ode_models import OdeSystem, get_ode_system, fn_system, hes1_system, lv_system, MODEL_IDS
 from .gaussian_process import GPCov, calculate_gp_covariances, mat2band
-from .samplers import run_hmc_sampler
+from .samplers import run_hmc_sampler, run_nuts_sampler, logdensity_func_wrapper, logdensity_and_gradient_func_wrapper
 from .solver import solve_magi
 from . import diagnostics, distributed, initialization
 from .target import MagiTarget, dimension, capabilities, logdensity, logdensity_and_gradient, LogDensityOrder
@@ -15,5 +15,5 @@ from .target import MagiTarget, dimension, capabilities, logdensity, logdensity_
 __all__ = [
     "Kernel", "create_matern52_kernel", "create_rbf_kernel", "create_general_matern_kernel", "OdeSystem", "get_ode_system", "fn_system", "hes1_system",
     "lv_system", "MODEL_IDS", "GPCov", "calculate_gp_covariances", "mat2band", "MagiTarget", "dimension", "capabilities",
-    "logdensity", "logdensity_and_gradient", "LogDensityOrder", "run_hmc_sampler", "solve_magi", "diagnostics", "distributed",
+    "logdensity", "logdensity_and_gradient", "LogDensityOrder", "run_hmc_sampler", "run_nuts_sampler", "logdensity_func_wrapper", "logdensity_and_gradient_func_wrapper", "solve_magi", "diagnostics", "distributed",
 ]

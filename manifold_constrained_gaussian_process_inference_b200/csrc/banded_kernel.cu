@@ -101,9 +101,9 @@ bool model_kx(int model, int& KX) {
     }
 }
 
-// layout of flow_logpost_kernel's shared memory (G = 2: 16 chains per block)
-size_t flow_smem_bytes(int D, int K, int KX, int n, int HB, int& RS0) {
-    const int NT = (n + 7) / 8, NP = (NT + 1) / 2, CH = 16, RED = 3 + K;
+// layout of flow_logpost_kernel's shared memory (G chain groups = 8 G chains per block)
+size_t flow_smem_bytes(int D, int K, int KX, int n, int HB, int G, int& RS0) {
+    const int NT = (n + 7) / 8, NP = (NT + 1) / 2, CH = 8 * G, RED = 3 + K;
     RS0 = (16 * NP + 8 * HB + 15) / 16 * 16;
     const size_t doubles = (size_t)3 * CH * D * RS0 + (size_t)D * NP * CH * RED + (size_t)2 * CH * (KX + 3 * D) + (size_t)CH * D * (RED + 4) + (size_t)D * 16 * NP;
     if (NP > 32) return (size_t)1 << 40;          // the final stage gives one lane to every tile pair

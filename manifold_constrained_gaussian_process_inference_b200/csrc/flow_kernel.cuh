@@ -516,9 +516,9 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) flow_logpost_kernel(const 
 #endif
 }
 
-template <int MODEL, int HB>
-static cudaError_t flow_launch_one(const FlowArgs& a, int grid, size_t smem_bytes, cudaStream_t st) {
-    auto kern = flow_logpost_kernel<MODEL, HB, 2>;
+template <int MODEL, int HB, int G>
+static cudaError_t flow_launch_g(const FlowArgs& a, int grid, size_t smem_bytes, cudaStream_t st) {
+    auto kern = flow_logpost_kernel<MODEL, HB, G>;
     static PerDeviceOnce once;       // per instantiation
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -526,6 +526,11 @@ static cudaError_t flow_launch_one(const FlowArgs& a, int grid, size_t smem_byte
     }
     kern<<<grid, 32 * kFlowWarps, smem_bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int MODEL, int HB>
+static cudaError_t flow_launch_one(const FlowArgs& a, int grid, size_t smem_bytes, cudaStream_t st) {
+    return a.G == 1 ? flow_launch_g<MODEL, HB, 1>(a, grid, smem_bytes, st) : flow_launch_g<MODEL, HB, 2>(a, grid, smem_bytes, st);
 }
 
 template <int MODEL>

@@ -37,6 +37,9 @@ struct HmcState {
     long long wcount = 0;
     double *draws = nullptr; long long draws_cap = 0, n_draws = 0;       // [n_draws][n_chains][k + D + 1]
     double *xsum = nullptr; long long xsum_count = 0;                    // per-chain running sum of vec(X) over kept draws
+    // X draws (solve_magi's x_sampled, src/MagiJl.jl:633-771): vec(X) of the first x_chains chains at every x_thin-th kept draw
+    double *xdraws = nullptr; long long xdraws_cap = 0, n_xdraws = 0;
+    int x_chains = 0, x_thin = 1;
     long long acc_count = 0;
 };
 
@@ -137,7 +140,7 @@ __global__ void hmc_kick_drift_kernel(HmcState s, int P) {
 struct HmcFinish {
     int adapt, store, n_draw_cols, nD, K, D, sigma_is_fixed;
     double delta, mu_scale;
-    int accumulate_window, accumulate_x;
+    int accumulate_window, accumulate_x, store_x;
 };
 
 // last half kick, Hamiltonian, accept/reject, dual averaging, draw storage (one block per chain)
@@ -195,6 +198,10 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
     }
     __syncthreads();
     if (f.accumulate_x) for (int i = threadIdx.x; i < f.nD; i += blockDim.x) s.xsum[(size_t)c * f.nD + i] += s.q[base + i];
+    if (f.store_x && c < s.x_chains) {
+        double* xo = s.xdraws + ((size_t)s.n_xdraws * s.x_chains + c) * f.nD;
+        for (int i = threadIdx.x; i < f.nD; i += blockDim.x) xo[i] = s.q[base + i];
+    }
     if (f.store && threadIdx.x < f.n_draw_cols) {
         double* out = s.draws + ((size_t)s.n_draws * s.n_chains + c) * f.n_draw_cols;
         const int j = threadIdx.x;
@@ -269,7 +276,7 @@ __global__ void fill_double_kernel(double* p, size_t nel, double v) {
 void hmc_free(magi_handle* h) {
     HmcState* s = (HmcState*)h->hmc;
     if (!s) return;
-    double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->wpart, s->draws, s->xsum};
+    double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->wpart, s->draws, s->xsum, s->xdraws};
     for (double* p : ptrs) if (p) cudaFree(p);
     if (s->n_div) cudaFree(s->n_div);
     delete s;
@@ -351,6 +358,16 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
             s->draws = nd; s->draws_cap = need;
         }
     }
+    if (store_draws && s->x_chains > 0) {
+        const long long need = s->n_xdraws + (n_iter + s->x_thin - 1) / s->x_thin + 1;
+        if (need > s->xdraws_cap) {
+            double* nd = nullptr;
+            const size_t per = (size_t)s->x_chains * h->n * h->D;
+            HCK(cudaMalloc(&nd, sizeof(double) * (size_t)need * per), "cudaMalloc X draws");
+            if (s->xdraws) { HCK(cudaMemcpyAsync(nd, s->xdraws, sizeof(double) * (size_t)s->n_xdraws * per, cudaMemcpyDeviceToDevice, st), "copy X draws"); HCK(cudaStreamSynchronize(st), "sync"); cudaFree(s->xdraws); }
+            s->xdraws = nd; s->xdraws_cap = need;
+        }
+    }
     // Stan-style windows over the warm-up: initial fast buffer, doubling slow windows, terminal fast buffer
     int init_buf = 75, term_buf = 50, base_win = 25;
     if (adapt && n_iter < 150) { init_buf = (int)(0.15 * n_iter); term_buf = (int)(0.10 * n_iter); base_win = n_iter - init_buf - term_buf; }
@@ -360,6 +377,8 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
     HmcFinish f;
     f.adapt = adapt; f.n_draw_cols = s->n_draw_cols; f.nD = h->n * h->D; f.K = h->K; f.D = h->D; f.sigma_is_fixed = h->sigma_is_fixed;
     f.delta = target_accept; f.mu_scale = 10.0;
+    h->dispatch_chains = s->n_chains_total > 0 ? s->n_chains_total : 0;      // the same K1 variant on every rank of a sharded run
+    struct DispatchReset { magi_handle* h; ~DispatchReset() { h->dispatch_chains = 0; } } dispatch_reset{h};
     for (int it = 0; it < n_iter; ++it) {
         hmc_prep_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s);
         hmc_begin_kernel<<<dim3(nc, 1), 256, 0, st>>>(*s, P);      // one block per chain (ordered reduction of the kinetic energy)
@@ -372,6 +391,7 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
         }
         const bool in_slow = adapt && it >= init_buf && it < n_iter - term_buf;
         f.store = store_draws; f.accumulate_window = in_slow ? 1 : 0; f.accumulate_x = store_draws ? 1 : 0;
+        f.store_x = (store_draws && s->x_chains > 0 && (s->n_draws % s->x_thin) == 0) ? 1 : 0;
         hmc_finish_kernel<<<nc, 256, 0, st>>>(*s, P, f);
         h->launches++;
         if (in_slow) {
@@ -379,6 +399,7 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
             h->launches++;
         }
         s->iter++;
+        if (f.store_x) s->n_xdraws++;
         if (store_draws) { s->n_draws++; s->xsum_count++; }
         s->acc_count++;
         if (in_slow) {
@@ -460,6 +481,29 @@ extern "C" int magi_hmc_allgather_draws(magi_handle* h, double* out_dev, void* s
     return comm_allgather(h, s->draws, out_dev, cnt, st);
 }
 
+// X draws: keep vec(X) (n*D doubles, time fastest) of the first n_chains_x chains at every thin-th kept iteration -- the x_sampled
+// field of solve_magi's result (src/MagiJl.jl:633-771).  Call after magi_hmc_init and before the kept iterations.
+extern "C" int magi_hmc_store_x(magi_handle* h, int n_chains_x, int thin) {
+    if (!h || !h->hmc || n_chains_x < 0 || thin < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_store_x: bad argument (call magi_hmc_init first)");
+    HmcState* s = (HmcState*)h->hmc;
+    if (s->n_xdraws > 0 && n_chains_x != s->x_chains) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_store_x: X draws of another chain count are already stored");
+    s->x_chains = n_chains_x < s->n_chains ? n_chains_x : s->n_chains;
+    s->x_thin = thin;
+    return MAGI_OK;
+}
+
+// out: [n_stored][n_chains_x][n*D]; returns the number of stored X draws and the chain count through the pointers
+extern "C" int magi_hmc_get_x_draws(magi_handle* h, double* out, long long max_draws, long long* n_stored, int* n_chains_x) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_get_x_draws: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    const long long ns = s->n_xdraws < max_draws ? s->n_xdraws : max_draws;
+    if (n_stored) *n_stored = s->n_xdraws;
+    if (n_chains_x) *n_chains_x = s->x_chains;
+    if (out && ns > 0) HCK(cudaMemcpy(out, s->xdraws, sizeof(double) * (size_t)ns * s->x_chains * h->n * h->D, cudaMemcpyDeviceToHost), "D2H X draws");
+    return MAGI_OK;
+}
+
 // per-chain statistics: mean acceptance probability, current step size, divergences; xmean = posterior mean of vec(X) per chain
 extern "C" int magi_hmc_get_stats(magi_handle* h, double* accept_rate, double* step_size, int* n_divergent, double* xmean, double* minv) {
     if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_get_stats: no sampler state");
@@ -495,6 +539,6 @@ extern "C" int magi_hmc_reset_stats(magi_handle* h) {
     HCK(cudaMemset(s->acc_sum, 0, sizeof(double) * s->n_chains), "memset");
     HCK(cudaMemset(s->n_div, 0, sizeof(int) * s->n_chains), "memset");
     HCK(cudaMemset(s->xsum, 0, sizeof(double) * (size_t)s->n_chains * h->n * h->D), "memset");
-    s->acc_count = 0; s->n_draws = 0; s->xsum_count = 0;
+    s->acc_count = 0; s->n_draws = 0; s->xsum_count = 0; s->n_xdraws = 0;
     return MAGI_OK;
 }

@@ -35,7 +35,7 @@ extern "C" int magi_destroy(magi_handle* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) free_dev(h->d_band[i]);
     for (int i = 0; i < 7; ++i) free_dev(h->d_dense[i]);
-    free_dev(h->d_fragtab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
+    free_dev(h->d_fragtab); free_dev(h->d_fragtab_nat); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
     free_dev(h->d_dense_work); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
     free_dev(h->d_small); free_dev(h->d_flow_units); if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -130,19 +130,22 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
 
     h->dense_mode = (h->geom.HB > kMaxHB) || h->model == MAGI_MODEL_L96;
     if (!h->dense_mode) {
-        size_t fsz = fragtab_doubles(h->n, h->b, h->D);
-        if (cudaMalloc(&h->d_fragtab, sizeof(double) * fsz) != cudaSuccess) return fail(set_error(MAGI_ERR_CUDA, "cudaMalloc fragment tables failed"));
         banded_pick_config(h->D, h->K, h->geom.NT, h->geom.HB, h->smem_limit, 4, h->G, h->H, h->DW, h->scratch_in_smem, h->smem_bytes);
-        // K1 variant: the windowed, warp-specialised kernel (banded_kernel.cuh) is the default; the dataflow kernel
-        // (flow_kernel.cuh) is available when X, E and KE of 16 chains fit shared memory and is selected with MAGI_K1=flow at
-        // create time (measured 8 % slower at 65 536 chains and 20 % slower at 4096 on FN n=201, profiles/README.md)
+        // K1 variants: the windowed, warp-specialised kernel (banded_kernel.cuh) for large batches, the dataflow kernel
+        // (flow_kernel.cuh: all 16 warps of a block work on 8 or 16 chains) for batches of at most one block per SM, where
+        // the windowed kernel leaves most warps of the machine idle -- when X, E and KE of a block fit shared memory.
+        // MAGI_K1=windowed|flow at create time forces one of them (development knob for A/B measurements).
         int KX = 0;
         model_kx(h->model, KX);
-        h->flow_smem = flow_smem_bytes(h->D, h->K, KX, h->n, h->geom.HB, h->flow_RS0);
+        for (int g = 1; g <= 2; ++g) {
+            h->flow_smem[g] = flow_smem_bytes(h->D, h->K, KX, h->n, h->geom.HB, g, h->flow_RS0);
+            h->flow_fits[g] = h->flow_smem[g] <= (size_t)prop.sharedMemPerBlockOptin;
+        }
         const char* force = getenv("MAGI_K1");
-        h->use_flow = h->flow_smem <= (size_t)prop.sharedMemPerBlockOptin && force && !strcmp(force, "flow");
-        if (force && !strcmp(force, "flow") && !h->use_flow) return fail(set_error(MAGI_ERR_UNSUPPORTED, "MAGI_K1=flow: the state of 16 chains does not fit shared memory"));
-        if (h->use_flow) {
+        h->flow_mode = (force && !strcmp(force, "flow")) ? 1 : ((force && !strcmp(force, "windowed")) ? -1 : 0);
+        if (h->flow_mode == 1 && !h->flow_fits[1]) return fail(set_error(MAGI_ERR_UNSUPPORTED, "MAGI_K1=flow: the state of 8 chains does not fit shared memory"));
+        if (!h->flow_fits[1]) h->flow_mode = -1;
+        if (h->flow_mode >= 0) {
             const char* ord = getenv("MAGI_FLOW_LAG");      // development knob: wavefront order with this extra lag
             std::vector<int> units = flow_unit_order(h->D, (h->geom.NT + 1) / 2, h->geom.HB, ord ? atoi(ord) : -1);
             h->flow_units = (int)units.size();
@@ -198,12 +201,28 @@ static int ensure_scratch(magi_handle* h, int n_chains) {
     return MAGI_OK;
 }
 
-int refresh_fragtab(magi_handle* h, cudaStream_t st) {
-    if (!h->frag_dirty || h->dense_mode) return MAGI_OK;
-    CK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], h->d_fragtab, h->n, h->b, h->D, h->use_flow,
+// Which K1 runs a batch of n_chains: 0 = windowed, else the dataflow kernel with that many chain groups per block.
+static int flow_groups_for(const magi_handle* h, int n_chains_call) {
+    if (h->flow_mode < 0) return 0;
+    const long long n_chains = h->dispatch_chains > 0 ? h->dispatch_chains : n_chains_call;
+    if (h->flow_mode > 0) return h->flow_fits[2] && n_chains > 8 * h->sm_count ? 2 : 1;
+    if (n_chains <= 8 * h->sm_count) return 1;
+    if (n_chains <= 16 * h->sm_count && h->flow_fits[2]) return 2;
+    return 0;
+}
+
+// The two kernels read differently ordered fragment tables (the windowed kernel permutes the output slots of a tile); one
+// buffer per layout, each built on first use and whenever the band tables change.
+int refresh_fragtab(magi_handle* h, bool natural, cudaStream_t st) {
+    if (h->dense_mode) return MAGI_OK;
+    double*& tab = natural ? h->d_fragtab_nat : h->d_fragtab;
+    bool& dirty = natural ? h->frag_nat_dirty : h->frag_dirty;
+    if (!tab) { CK(cudaMalloc(&tab, sizeof(double) * fragtab_doubles(h->n, h->b, h->D)), "cudaMalloc fragment tables"); dirty = true; }
+    if (!dirty) return MAGI_OK;
+    CK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], tab, h->n, h->b, h->D, natural,
                             1.0 / h->beta[1], 1.0 / h->beta[0], st), "build_fragtab");      // 1/beta2 folded into C~, 1/beta1 into K~
     h->launches++;
-    h->frag_dirty = false;
+    dirty = false;
     return MAGI_OK;
 }
 
@@ -212,15 +231,17 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     if (n_chains <= 0) return MAGI_OK;
     if (!h->tables_ready) return set_error(MAGI_ERR_NOT_READY, "band tables are neither built nor fully injected (magi_set_band_tables for every dim and table)");
     if (h->dense_mode) return eval_dense_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
-    int rc = refresh_fragtab(h, st);
+    const int fg = flow_groups_for(h, n_chains);
+    int rc = refresh_fragtab(h, fg > 0, st);
     if (rc) return rc;
-    if (h->use_flow) {
+    if (fg > 0) {
         FlowArgs f;
+        f.G = fg;
         f.n = h->n; f.P = h->P; f.n_chains = n_chains; f.NP = (h->geom.NT + 1) / 2; f.RS0 = h->flow_RS0; f.n_units = h->flow_units;
-        f.n_cblocks = (n_chains + 15) / 16;
+        f.n_cblocks = (n_chains + 8 * fg - 1) / (8 * fg);
         f.sigma_is_fixed = h->sigma_is_fixed; f.sigma_invalid = h->sigma_invalid;
         f.pitch = pitch; f.params = params_dev; f.ll = ll_dev; f.grad = grad_dev;
-        f.fragtab = h->d_fragtab; f.units = h->d_flow_units; f.yobs = h->d_yobs; f.nobs = h->d_nobs; f.sigma_init = h->d_sigma_init;
+        f.fragtab = h->d_fragtab_nat; f.units = h->d_flow_units; f.yobs = h->d_yobs; f.nobs = h->d_nobs; f.sigma_init = h->d_sigma_init;
         for (int i = 0; i < 3; ++i) { f.beta[i] = h->beta[i]; f.inv_beta[i] = 1.0 / h->beta[i]; }
         const int grid = f.n_cblocks < h->sm_count ? f.n_cblocks : h->sm_count;
         f.dbg = nullptr;
@@ -228,7 +249,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
         static const bool dbg_flow = getenv("MAGI_DBG_CLOCKS") != nullptr;
         long long* d_dbgf = nullptr;
         if (dbg_flow) { cudaMalloc(&d_dbgf, sizeof(long long) * 16 * 16 * grid); cudaMemset(d_dbgf, 0, sizeof(long long) * 16 * 16 * grid); f.dbg = d_dbgf; }
-        CK(launch_flow_cfg(h->model, f, h->geom.HB, grid, h->flow_smem, st), "flow_logpost_kernel launch");
+        CK(launch_flow_cfg(h->model, f, h->geom.HB, grid, h->flow_smem[fg], st), "flow_logpost_kernel launch");
         h->launches++;
         if (dbg_flow) {
             cudaStreamSynchronize(st);
@@ -308,11 +329,15 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
     { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
     const int per = nchunks > 0 ? ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32 : n_chains;
-    if (!h->dense_mode && !h->use_flow && h->tables_ready) select_block_shape(h, per);      // the shape every chunk will run with
-    if (n_chains >= 2 * chunk_min && !h->dense_mode && (h->scratch_in_smem || h->use_flow) && h->tables_ready) {
+    // the K1 variant is chosen by the size of the CALL, not of its chunks: how a batch is cut into chunks never changes the result
+    struct DispatchPin { magi_handle* h; long long old; ~DispatchPin() { h->dispatch_chains = old; } } pin{h, h->dispatch_chains};
+    if (h->dispatch_chains == 0) h->dispatch_chains = n_chains;
+    const bool chunk_flow = !h->dense_mode && flow_groups_for(h, per) > 0;
+    if (!h->dense_mode && !chunk_flow && h->tables_ready) select_block_shape(h, per);      // the shape every chunk will run with
+    if (n_chains >= 2 * chunk_min && !h->dense_mode && (h->scratch_in_smem || chunk_flow) && h->tables_ready) {
         for (int i = 0; i < 3; ++i)
             if (!h->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
-        rc = refresh_fragtab(h, h->stream);
+        rc = refresh_fragtab(h, chunk_flow, h->stream);
         if (rc) return rc;
         CK(cudaStreamSynchronize(h->stream), "stream sync");
         int i = 0;
@@ -392,7 +417,7 @@ extern "C" int magi_set_band_tables(magi_handle* h, int dim, int which, const do
     const int t = which - MAGI_MAT_CINV_BAND;
     CK(cudaMemcpy(h->d_band[t] + (size_t)dim * tab, in, sizeof(double) * tab, cudaMemcpyHostToDevice), "H2D band table");
     h->band_set[(size_t)t * h->D + dim] = 1;
-    h->frag_dirty = true;
+    h->frag_dirty = true; h->frag_nat_dirty = true;
     h->dense_band_dirty = true;
     bool all = true;
     for (char c : h->band_set) all = all && c;

@@ -74,7 +74,7 @@ struct BandedArgs {
 
 // arguments of the dataflow K1 (flow_kernel.cuh)
 struct FlowArgs {
-    int n, P, n_chains, NP, RS0, n_units, n_cblocks, sigma_is_fixed, sigma_invalid, stagger;
+    int n, P, n_chains, NP, RS0, n_units, n_cblocks, sigma_is_fixed, sigma_invalid, stagger, G;
     long long pitch;
     const double* params;
     double* ll;
@@ -93,7 +93,7 @@ struct FlowArgs {
 cudaError_t launch_build_fragtab(const double* band_cinv, const double* band_mphi, const double* band_kinv, double* fragtab,
                                  int n, int b, int D, bool natural, double scale_c, double scale_k, cudaStream_t st);
 // dataflow K1: shared-memory footprint for 16 chains (0: does not apply), row stride, wavefront unit order
-size_t flow_smem_bytes(int D, int K, int KX, int n, int HB, int& RS0);
+size_t flow_smem_bytes(int D, int K, int KX, int n, int HB, int G, int& RS0);
 std::vector<int> flow_unit_order(int D, int NP, int HB, int extra_lag);
 bool model_kx(int model, int& KX);
 size_t fragtab_doubles(int n, int b, int D);

@@ -13,12 +13,13 @@ struct magi_handle {
     double* d_band[3] = {nullptr, nullptr, nullptr};
     // dense GPCov fields (C, Cinv, Cprime, Cdoubleprime, mphi, Kphi, Kinv), each D x n x n column-major; only after a device setup
     double* d_dense[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double* d_fragtab = nullptr;
+    double* d_fragtab = nullptr;       // windowed kernel's layout
+    double* d_fragtab_nat = nullptr;   // dataflow kernel's (natural) layout
     double* d_yobs = nullptr;
     int* d_nobs = nullptr;
     double* d_sigma_init = nullptr;
     std::vector<char> band_set;
-    bool tables_ready = false, frag_dirty = true, dense_band_dirty = true;
+    bool tables_ready = false, frag_dirty = true, frag_nat_dirty = true, dense_band_dirty = true;
     bool dense_mode = false;
     // host-API staging
     double *d_params = nullptr, *d_ll = nullptr, *d_grad = nullptr;
@@ -42,9 +43,12 @@ struct magi_handle {
     int G = 2, H = 1, DW = 1, scratch_in_smem = 1, gmax_cur = 4;
     size_t smem_bytes = 0;
     // dataflow K1 (flow_kernel.cuh): chosen at create when the state of 16 chains fits shared memory
-    bool use_flow = false;
+    long long dispatch_chains = 0;     // > 0: choose the K1 variant as for a batch of this many chains (the sampler sets the GLOBAL
+                                       // chain count of a multi-rank run, so that every sharding runs the same kernel: bit-identical draws)
+    int flow_mode = 0;                 // 0: by batch size (small batches), 1: always (MAGI_K1=flow), -1: never (MAGI_K1=windowed)
+    bool flow_fits[3] = {false, false, false};      // [G]: the state of 8 G chains fits shared memory
     int flow_RS0 = 0, flow_units = 0;
-    size_t flow_smem = 0;
+    size_t flow_smem[3] = {0, 0, 0};
     int* d_flow_units = nullptr;
     std::vector<int> repaired_c, repaired_k;
     double setup_alloc_ms = 0.0, setup_kernel_ms = 0.0;   // device setup: host time in cudaMalloc / device time of K3-K6
@@ -59,7 +63,7 @@ namespace magi {
 int set_error(int code, const std::string& msg);
 int cuda_error(cudaError_t e, const char* what);
 int ensure_capacity(magi_handle* h, int n_chains);
-int refresh_fragtab(magi_handle* h, cudaStream_t st);
+int refresh_fragtab(magi_handle* h, bool natural, cudaStream_t st);
 int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int eval_dense_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int run_device_setup(magi_handle* h);

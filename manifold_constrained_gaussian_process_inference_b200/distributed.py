@@ -102,9 +102,10 @@ def init_device_comm(target, group=None):
     _lib.check(L.magi_comm_warmup(target._h, None))
 
 
-def allgather_draws_device(target, stream: int = 0):
+def allgather_draws_device(target, stream: int = 0, out=None):
     """All-gather of the on-device draw store over the library's communicator (``init_device_comm``): returns a CUDA tensor
-    (n_iter, n_chains_total, n_cols) with chains in global order.  Every rank must hold equally many chains."""
+    (n_iter, n_chains_total, n_cols) with chains in global order.  Every rank must hold equally many chains.  ``out``: optional
+    preallocated (world, n_iter, n_local, n_cols) float64 CUDA tensor to receive the ranks' blocks."""
     import ctypes
     import torch
     from . import _lib
@@ -113,6 +114,8 @@ def allgather_draws_device(target, stream: int = 0):
     _, ns, nc, ncol = hmc_draws_device_view(target)
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
-    out = torch.empty((world, ns, nc, ncol), dtype=torch.float64, device="cuda:%d" % target.device)
+    if out is None:
+        out = torch.empty((world, ns, nc, ncol), dtype=torch.float64, device="cuda:%d" % target.device)
+    assert tuple(out.shape) == (world, ns, nc, ncol) and out.is_contiguous()
     _lib.check(L.magi_hmc_allgather_draws(target._h, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)))
     return out.permute(1, 0, 2, 3).reshape(ns, world * nc, ncol)

@@ -4,8 +4,9 @@ Kept from the reference: the config keys and defaults (:kernel "matern52", :nite
 :stepSizeFactor 0.01, :bandSize 20, :priorTemperature [1,1,1], :jitter 1e-6, :targetAcceptRatio 0.8, :sigma, :phi, :xInit,
 :thetaInit; :208-220), ``sigma_is_fixed = :sigma and :phi both given`` (:224), linear-interpolation X init (:351-410),
 bounds-based θ init (:412-453), band clamp (:459), parameter vector layout [vec(X); θ; log σ] (:526-569), burn-in split
-(:578-581) and the shape of the result (θ, σ, lp; :633-771).  New keys: :nChains (independent chains, default 1024),
-:nLeapfrog (static trajectory length), :setupMode, :seed, :device.
+(:578-581) and the shape of the result (θ, x_sampled, σ, φ, lp; :633-771).  New keys: :nChains (independent chains, default 1024),
+:nLeapfrog (static trajectory length), :setupMode, :seed, :device, :xChains (chains whose latent trajectories are kept, default
+min(nChains, 16)), :xThin (keep X at every xThin-th kept iteration, default 1).
 
 When ``config['phi']`` and/or ``config['sigma']`` are absent they are estimated per dimension by minimising the GP negative log
 marginal likelihood (src/MagiJl.jl:254-330 -> src/initialization.jl), objective on the GPU, Nelder-Mead on the host
@@ -144,14 +145,18 @@ def solve_magi(y_obs, t_obs, ode_system: OdeSystem, config=None, initial_params=
         rng = np.random.default_rng(int(get("seed", 0)))
         p0 = p0[None, :] + 0.01 * rng.normal(size=(n_chains, P)) * np.maximum(1.0, np.abs(p0))[None, :] * (np.arange(n_chains) > 0)[:, None]
     n_adapts = int(np.floor(niter * burn))                                 # :578
+    x_chains = int(get("xChains", min(n_chains, 16)))
     chain, stats = run_hmc_sampler(target, p0, n_samples=niter, n_adapts=n_adapts, target_accept_ratio=delta,
-                                   initial_step_size=eps0, n_leapfrog=n_leap, seed=int(get("seed", 0)))
+                                   initial_step_size=eps0, n_leapfrog=n_leap, seed=int(get("seed", 0)),
+                                   x_chains=x_chains, x_thin=int(get("xThin", 1)))
     theta = chain[:, :, :k]
     sig = chain[:, :, k:k + D]
     if sigma_is_fixed:
         sig = np.broadcast_to(sigma_init[None, None, :], sig.shape).copy() # repeated rows (:696)
     lp = chain[:, :, k + D]
-    if n_chains == 1:
+    x_sampled = stats.get("x_sampled")                                      # (S', xChains, n, D); S' = S when xThin == 1
+    if n_chains == 1:                                                       # the reference's shapes: S×k, S×n×D, S×D, S (:633-771)
         theta, sig, lp = theta[:, 0], sig[:, 0], lp[:, 0]
-    return dict(theta=theta, sigma=sig, phi=phi, lp=lp, x_mean=stats["x_mean"].reshape(n_chains, D, n).transpose(0, 2, 1),
-                stats=stats, target=target)
+        x_sampled = x_sampled[:, 0] if x_sampled is not None else None
+    return dict(theta=theta, x_sampled=x_sampled, sigma=sig, phi=phi, lp=lp,
+                x_mean=stats["x_mean"].reshape(n_chains, D, n).transpose(0, 2, 1), stats=stats, target=target)

@@ -1,6 +1,7 @@
-"""Both K1 kernels against the oracle and against each other.  `magi_create` picks the dataflow kernel (flow_kernel.cuh) when
-the state of 16 chains fits shared memory and the windowed kernel (banded_kernel.cuh) otherwise; MAGI_K1 forces one at create
-time (development knob), so every shape below runs through both code paths on identical inputs.
+"""Both K1 kernels against the oracle and against each other.  The library runs small batches (at most one block per SM) on the
+dataflow kernel (flow_kernel.cuh; 8 or 16 chains per block) when the state of a block fits shared memory, everything else on
+the windowed kernel (banded_kernel.cuh); MAGI_K1 forces one at create time (development knob), so every shape below runs through
+both code paths on identical inputs.
 Tolerance: tests/helpers.py (1e-10 relative)."""
 import numpy as np
 import pytest
@@ -28,6 +29,7 @@ def _target(pkg, prob, monkeypatch, variant):
     ("lv", 81, 20, 10, {"T": 4.0}),
     ("hes1", 33, 5, 13, {}),                                 # D = 3
     ("hes1", 64, 12, 20, {}),
+    ("fn", 397, 20, 11, {"beta": (1.0, 1.0, 5.0), "obs_every": 4, "T": 20.0}),   # BASELINE config 1 shape: 8 chains per block only
 ])
 def test_flow_and_windowed_kernels_match_the_oracle(pkg, monkeypatch, model, n, b, nc, kw):
     prob = H.make_problem(model=model, n=n, b=b, n_chains=nc, seed=7 * n + b, **kw)
@@ -80,3 +82,22 @@ def test_flow_kernel_guards_are_per_chain(pkg, monkeypatch):
     assert np.array_equal(ll[keep], ll0[keep]) and np.array_equal(g[keep], g0[keep])
     ll_ref, g_ref = H.oracle_batched(prob, bad)
     H.assert_parity(ll, g, ll_ref, g_ref, "guards")
+
+
+@pytest.mark.parametrize("nc", [1, 8 * 148, 8 * 148 + 1, 16 * 148, 16 * 148 + 1])
+def test_dispatch_by_batch_size_is_seamless(pkg, monkeypatch, nc):
+    """Default dispatch: <= 8 chains per SM -> dataflow kernel with 8 chains per block, <= 16 per SM -> 16 chains per block,
+    beyond -> windowed kernel.  Same chains, same values to rounding on either side of every switch; a sample against the oracle."""
+    monkeypatch.delenv("MAGI_K1", raising=False)
+    base = H.make_problem(model="fn", n=201, b=20, n_chains=8, seed=17, T=20.0, obs_every=5)
+    rng = np.random.default_rng(nc)
+    params = np.repeat(base["params"], (nc + 7) // 8, axis=0)[:nc] + 1e-3 * rng.normal(size=(nc, base["params"].shape[1]))
+    tg = H.cuda_target(pkg, base)
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    idx = np.unique(np.concatenate([[0, nc // 2, nc - 1], rng.integers(0, nc, size=5)]))
+    ll_ref, g_ref = H.oracle_batched(base, params[idx])
+    H.assert_parity(ll[idx], g[idx], ll_ref, g_ref, "default dispatch, %d chains" % nc)
+    monkeypatch.setenv("MAGI_K1", "windowed")
+    tw = H.cuda_target(pkg, base)
+    llw, gw = tw.logdensity_and_gradient_batched(params)
+    H.assert_parity(ll, g, llw, gw, "default dispatch vs windowed, %d chains" % nc)

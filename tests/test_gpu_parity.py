@@ -208,9 +208,10 @@ def test_lorenz96_dense_path(pkg):
     H.assert_parity(ll, g, ll_ref, g_ref, "lorenz96")
 
 
-def test_pipelined_host_call_matches_single_stream(pkg):
+def test_pipelined_host_call_matches_single_stream(pkg, monkeypatch):
     """Batches >= 2048 chains go through the chunked H2D / kernel / D2H pipeline: results must be bit-identical to
-    evaluating the same chains in small calls."""
+    evaluating the same chains in small calls (with the kernel variant pinned: the library picks it by the size of the call)."""
+    monkeypatch.setenv("MAGI_K1", "windowed")
     prob = H.make_problem(n=41, T=8.0, b=6, n_chains=8, seed=21)
     tg = H.cuda_target(pkg, prob)
     rng = np.random.default_rng(0)

@@ -17,6 +17,8 @@ ap.add_argument("--chains", type=int, default=65536)
 ap.add_argument("--iters", type=int, default=40)
 ap.add_argument("--warmup", type=int, default=20)
 ap.add_argument("--leapfrog", type=int, default=10)
+ap.add_argument("--n", type=int, default=201, help="discretisation points (201 = BASELINE config 5; smaller grids converge within a short run)")
+ap.add_argument("--step", type=float, default=0.002)
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -24,6 +26,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 first, n_local = D.shard_chains(args.chains, rank, world)
 # every rank draws the SAME global chain population and keeps its slice: results do not depend on the world size
+if args.n != 201:
+    synthetic.CONFIGS["fn201"] = dict(synthetic.CONFIGS["fn201"], n=args.n, obs_every=max(1, (args.n - 1) // 40))
 work = synthetic.make_workload("fn201", args.chains, rank=0)
 params = work["params"][first:first + n_local]
 tg = pkg.MagiTarget.from_config(work["yobs"], work["tvec"], work["phi"], pkg.fn_system(), work["sigma_init"], bandsize=20, jitter=1e-6,
@@ -31,7 +35,7 @@ tg = pkg.MagiTarget.from_config(work["yobs"], work["tvec"], work["phi"], pkg.fn_
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 t0 = time.perf_counter()
-chain, st = pkg.run_hmc_sampler(tg, params, n_samples=args.iters, n_adapts=args.warmup, initial_step_size=0.002, n_leapfrog=args.leapfrog,
+chain, st = pkg.run_hmc_sampler(tg, params, n_samples=args.iters, n_adapts=args.warmup, initial_step_size=args.step, n_leapfrog=args.leapfrog,
                                 seed=20251018 + 5, chain_id_offset=first, keep_on_device=True, n_chains_total=args.chains,
                                 window_allreduce=D.make_window_allreduce(tg) if world > 1 else None)
 torch.cuda.synchronize()
