@@ -109,101 +109,155 @@ struct DenseGradArgs {
     const double *E, *KE, *CX, *MT;
     const double* yobs; const int* nobs; const double* sigma_init;
     double beta[3], inv_beta[3];
+    double* part;       // [n_chains][D][4 + K]: e.Ke, x.Cx, sse, bad flag, theta-gradient partials of one (chain, dimension)
 };
 
+// Gradient with respect to the states of ONE (chain, dimension) and that dimension's partial sums (likelihoods.jl:139-221);
+// grid (n_chains, D): a model with 64 components gives 64 blocks per chain instead of one block looping over the dimensions.
 template <int MODEL>
-__global__ void __launch_bounds__(256) dense_grad_kernel(const DenseGradArgs a) {
+__global__ void __launch_bounds__(256) dense_grad_part_kernel(const DenseGradArgs a) {
     constexpr int K = DenseOde<MODEL>::K;
     __shared__ double sh[8];
-    __shared__ int sbad;
-    const int c = blockIdx.x, n = a.n, D = a.D;
+    const int c = blockIdx.x, d = blockIdx.y, n = a.n, D = a.D;
+    if (a.sigma_invalid) return;                                      // (the finalize kernel writes -Inf / NaN, interface.jl:192-195)
     const double* xp = a.params + (size_t)c * a.pitch;
     double* gp = a.grad ? a.grad + (size_t)c * a.pitch : nullptr;
     const size_t plane = (size_t)n * a.n_chains, base = (size_t)c * n;
+    const int nxt = n * D + K;
+    double th[DenseOde<MODEL>::KX];
+#pragma unroll
+    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    DenseOde<MODEL>::prepare(th);
+    const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
+    double gth[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) gth[i] = 0.0;
+    double s;
+    if (a.sigma_is_fixed) s = a.sigma_init[d];
+    else {
+        const double raw = xp[nxt + d];
+        s = isnan(raw) ? raw : exp(fmin(fmax(raw, -15.0), 15.0));     // interface.jl:200
+    }
+    const double inv_sig2 = 1.0 / (s * s);
+    const double* Ed = a.E + (size_t)d * plane + base;
+    const double* KEd = a.KE + (size_t)d * plane + base;
+    const double* CXd = a.CX + (size_t)d * plane + base;
+    const double* MTd = a.MT + (size_t)d * plane + base;
+    const double* yd = a.yobs + (size_t)d * n;
+    double eke = 0.0, xcx = 0.0, sse = 0.0;
+    bool bad = false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
+        auto w = [&](int dd) { return a.KE[(size_t)dd * plane + base + i] * inv_b1; };   // likelihoods.jl:201
+        const double xdv = xp[(size_t)d * n + i], y = yd[i], cx = CXd[i], ke = KEd[i];
+        const bool fin = isfinite(y);
+        const double e0 = fin ? xdv - y : 0.0;
+        double gv = 0.0;
+        if (fin) gv -= (e0 * inv_sig2) * inv_b3;                   // likelihoods.jl:179
+        gv -= cx * inv_b2;                                         // :186
+        gv += MTd[i] * inv_b1;                                     // :194
+        DenseOde<MODEL>::jx_col_sub(d, x, w, th, D, gv);           // :214-216
+        DenseOde<MODEL>::jth_row_sub(d, x, th, D, ke * inv_b1, gth);   // :219-221
+        eke += Ed[i] * ke;
+        xcx += xdv * cx;
+        sse += e0 * e0;
+        bad |= gp && !isfinite(gv);            // value-only calls look at the log density alone (interface.jl:155-160)
+        if (gp) gp[(size_t)d * n + i] = gv;
+    }
+    eke = block_sum(eke, sh); xcx = block_sum(xcx, sh); sse = block_sum(sse, sh);
+    const double nbad = block_sum(bad ? 1.0 : 0.0, sh);
+#pragma unroll
+    for (int i = 0; i < K; ++i) gth[i] = block_sum(gth[i], sh);
+    if (threadIdx.x == 0) {
+        double* r = a.part + ((size_t)c * D + d) * (4 + K);
+        r[0] = eke; r[1] = xcx; r[2] = sse; r[3] = nbad;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r[4 + i] = gth[i];
+    }
+}
+
+// Per chain: the log density in the reference's order of accumulation over the dimensions, sigma gradient, log-sigma
+// transform, guards (interface.jl:192-264); the per-dimension terms (log, divisions) are formed by D threads in parallel.
+template <int MODEL>
+__global__ void __launch_bounds__(256) dense_finalize_kernel(const DenseGradArgs a) {
+    constexpr int K = DenseOde<MODEL>::K;
+    extern __shared__ double fin[];                                   // [D][4]: ll_obs / beta3, -eke / 2 beta1, -xcx / 2 beta2, d/d log sigma
+    __shared__ int sflag;
+    const int c = blockIdx.x, n = a.n, D = a.D;
+    const double* xp = a.params + (size_t)c * a.pitch;
+    double* gp = a.grad ? a.grad + (size_t)c * a.pitch : nullptr;
     const int nxt = n * D + K, P = a.P;
     if (a.sigma_invalid) {                                            // interface.jl:192-195
         if (threadIdx.x == 0) a.ll[c] = -INFINITY;
         if (gp) for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = NAN;
         return;
     }
-    double th[DenseOde<MODEL>::KX];
-#pragma unroll
-    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
-    DenseOde<MODEL>::prepare(th);
-    if (threadIdx.x == 0) sbad = 0;
-    const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
-    double gth[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) gth[i] = 0.0;
-    double ll = 0.0, prior = 0.0;
-    bool bad = false, bad2 = false;
-    for (int d = 0; d < D; ++d) {
+    if (threadIdx.x == 0) sflag = 0;
+    __syncthreads();
+    int flag = 0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const double* r = a.part + ((size_t)c * D + d) * (4 + K);
         double s;
         if (a.sigma_is_fixed) s = a.sigma_init[d];
         else {
             const double raw = xp[nxt + d];
-            const double cl = fmin(fmax(raw, -15.0), 15.0);           // interface.jl:200
-            s = isnan(raw) ? raw : exp(cl);
-            prior += isnan(raw) ? raw : cl;
+            s = isnan(raw) ? raw : exp(fmin(fmax(raw, -15.0), 15.0));
         }
-        const double s2 = s * s, inv_sig2 = 1.0 / s2;
-        const double* Ed = a.E + (size_t)d * plane + base;
-        const double* KEd = a.KE + (size_t)d * plane + base;
-        const double* CXd = a.CX + (size_t)d * plane + base;
-        const double* MTd = a.MT + (size_t)d * plane + base;
-        const double* yd = a.yobs + (size_t)d * n;
-        double eke = 0.0, xcx = 0.0, sse = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            auto x = [&](int dd) { return xp[(size_t)dd * n + i]; };
-            auto w = [&](int dd) { return a.KE[(size_t)dd * plane + base + i] * inv_b1; };   // likelihoods.jl:201
-            const double xdv = xp[(size_t)d * n + i], y = yd[i], cx = CXd[i], ke = KEd[i];
-            const bool fin = isfinite(y);
-            const double e0 = fin ? xdv - y : 0.0;
-            double gv = 0.0;
-            if (fin) gv -= (e0 * inv_sig2) * inv_b3;                   // likelihoods.jl:179
-            gv -= cx * inv_b2;                                         // :186
-            gv += MTd[i] * inv_b1;                                     // :194
-            DenseOde<MODEL>::jx_col_sub(d, x, w, th, D, gv);           // :214-216
-            DenseOde<MODEL>::jth_row_sub(d, x, th, D, ke * inv_b1, gth);   // :219-221
-            eke += Ed[i] * ke;
-            xcx += xdv * cx;
-            sse += e0 * e0;
-            bad |= gp && !isfinite(gv);            // value-only calls look at the log density alone (interface.jl:155-160)
-            if (gp) gp[(size_t)d * n + i] = gv;
-        }
-        eke = block_sum(eke, sh); xcx = block_sum(xcx, sh); sse = block_sum(sse, sh);
+        const double s2 = s * s, sse = r[2];
         const int nobs = a.nobs[d];
-        double ll_obs = -0.5 * sse / s2;                               // likelihoods.jl:139
-        if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);    // :141
-        ll += ll_obs / a.beta[2];
-        ll += (-0.5 * eke) / a.beta[0];
-        ll += (-0.5 * xcx) / a.beta[1];
+        double ll_obs = -0.5 * sse / s2;                              // likelihoods.jl:139
+        if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);   // :141
+        fin[4 * d + 0] = ll_obs / a.beta[2];                          // :143
+        fin[4 * d + 1] = (-0.5 * r[0]) / a.beta[0];                   // :146-147
+        fin[4 * d + 2] = (-0.5 * r[1]) / a.beta[1];                   // :150-151
         const double gsig = (s > 0 && nobs > 0) ? (sse / s2 - nobs) / (s * a.beta[2]) : 0.0;   // :229-246
-        bad |= gp && !isfinite(gsig);
-        if (!a.sigma_is_fixed) {
-            const double gls = gsig * s + 1.0;                         // interface.jl:249-253
-            bad2 |= !isfinite(gls);
-            if (gp && threadIdx.x == 0) gp[nxt + d] = gls;
-        }
+        const double gls = gsig * s + 1.0;                            // interface.jl:249-253
+        fin[4 * d + 3] = gls;
+        if (r[3] != 0.0 || (gp && !isfinite(gsig))) flag |= 1;
+        if (!a.sigma_is_fixed && !isfinite(gls)) flag |= 2;
     }
-#pragma unroll
-    for (int i = 0; i < K; ++i) { gth[i] = block_sum(gth[i], sh); bad |= gp && !isfinite(gth[i]); }
-    bad |= !isfinite(ll);
-    if (bad) atomicOr(&sbad, 1);
-    if (bad2) atomicOr(&sbad, 2);
+    if (flag) atomicOr(&sflag, flag);
     __syncthreads();
-    const int fl = sbad;
+    __shared__ double s_ll;
+    static_assert(K <= 16, "theta gradient staging");
+    __shared__ double s_gth[16];
+    if (threadIdx.x == 0) {
+        double ll = 0.0, prior = 0.0, gth[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) gth[i] = 0.0;
+        for (int d = 0; d < D; ++d) {                                 // the reference's order of accumulation
+            ll += fin[4 * d + 0]; ll += fin[4 * d + 1]; ll += fin[4 * d + 2];
+            const double* r = a.part + ((size_t)c * D + d) * (4 + K);
+#pragma unroll
+            for (int i = 0; i < K; ++i) gth[i] += r[4 + i];
+            if (!a.sigma_is_fixed) {
+                const double raw = xp[nxt + d];
+                prior += isnan(raw) ? raw : fmin(fmax(raw, -15.0), 15.0);   // interface.jl:206
+            }
+        }
+        bool bad = !isfinite(ll);
+        if (gp) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) bad |= !isfinite(gth[i]);
+        }
+        if (bad) atomicOr(&sflag, 1);
+        s_ll = a.sigma_is_fixed ? ll : ll + prior;
+#pragma unroll
+        for (int i = 0; i < K; ++i) s_gth[i] = gth[i];
+    }
+    __syncthreads();
+    const int fl = sflag;
     if (fl & 1) {                                                      // interface.jl:222-226
         if (threadIdx.x == 0) a.ll[c] = -INFINITY;
         if (gp) for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = 0.0;
         return;
     }
-    if (threadIdx.x == 0) a.ll[c] = a.sigma_is_fixed ? ll : ll + prior;
+    if (threadIdx.x == 0) a.ll[c] = s_ll;
     if (gp) {
         if (fl & 2) { for (int i = threadIdx.x; i < P; i += blockDim.x) gp[i] = 0.0; }   // interface.jl:260-264
-        else if (threadIdx.x == 0) {
-#pragma unroll
-            for (int i = 0; i < K; ++i) gp[n * D + i] = gth[i];
+        else {
+            for (int i = threadIdx.x; i < K; i += blockDim.x) gp[n * D + i] = s_gth[i];
+            if (!a.sigma_is_fixed) for (int d = threadIdx.x; d < D; d += blockDim.x) gp[nxt + d] = fin[4 * d + 3];
         }
     }
 }
@@ -220,7 +274,17 @@ static int dense_pointwise(magi_handle* h, int n_chains, const double* params, l
         a.pitch = pitch; a.params = params; a.ll = ll; a.grad = grad; a.E = E; a.KE = KE; a.CX = CX; a.MT = MT;
         a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
         for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
-        dense_grad_kernel<MODEL><<<n_chains, 256, 0, st>>>(a);
+        const size_t need = (size_t)n_chains * h->D * (4 + h->K);
+        if (need > h->dense_part_cap) {
+            if (h->d_dense_part) cudaFree(h->d_dense_part);
+            h->d_dense_part = nullptr; h->dense_part_cap = 0;
+            DCK(cudaMalloc(&h->d_dense_part, sizeof(double) * need), "cudaMalloc per-dimension partial sums");
+            h->dense_part_cap = need;
+        }
+        a.part = h->d_dense_part;
+        dense_grad_part_kernel<MODEL><<<dim3(n_chains, h->D), 256, 0, st>>>(a);
+        dense_finalize_kernel<MODEL><<<n_chains, 256, sizeof(double) * 4 * h->D, st>>>(a);
+        h->launches++;
     }
     DCK(cudaGetLastError(), "dense pointwise kernel");
     h->launches++;
@@ -238,7 +302,43 @@ static int dense_pointwise_dispatch(magi_handle* h, int n_chains, const double* 
     }
 }
 
+// Many-component models with a band the DMMA tiling covers (half-width <= 32): the four products per dimension as band
+// products on the fragment tables (band_product.cu) instead of band-truncated GEMMs; same pointwise stages.
+static int eval_band_products_dev(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad, cudaStream_t st) {
+    const int n = h->n, D = h->D;
+    const size_t plane = (size_t)n * n_chains;
+    if (!h->d_fragtab_bp) { DCK(cudaMalloc(&h->d_fragtab_bp, sizeof(double) * fragtab_doubles(n, h->b, D)), "cudaMalloc fragment tables"); h->frag_bp_dirty = true; }
+    if (h->frag_bp_dirty) {
+        DCK(launch_build_fragtab(h->d_band[0], h->d_band[1], h->d_band[2], h->d_fragtab_bp, n, h->b, D, true, 1.0, 1.0, st), "build_fragtab");
+        h->launches++; h->frag_bp_dirty = false;
+    }
+    const size_t need = 4 * plane * D;
+    if (need > h->dense_work_cap) {
+        if (h->d_dense_work) cudaFree(h->d_dense_work);
+        h->d_dense_work = nullptr; h->dense_work_cap = 0;
+        DCK(cudaMalloc(&h->d_dense_work, sizeof(double) * need), "cudaMalloc work space");
+        h->dense_work_cap = need;
+    }
+    double* MXE = h->d_dense_work;            // MX, then E in place
+    double* KE = MXE + plane * D;
+    double* CX = KE + plane * D;
+    double* MT = CX + plane * D;
+    auto bp = [&](int view, const double* in, long long cs, long long ds, double* out) {
+        cudaError_t e = launch_band_product(h->d_fragtab_bp, view, in, cs, ds, out, (long long)plane, n, h->b, D, n_chains, h->sm_count, st);
+        h->launches++;
+        return e;
+    };
+    DCK(bp(0, params, pitch, n, MXE), "band product m~ X");                      // likelihoods.jl:129
+    DCK(bp(1, params, pitch, n, CX), "band product C~ X");                       // :133
+    int rc = dense_pointwise_dispatch(h, n_chains, params, pitch, ll, grad, MXE, MXE, nullptr, nullptr, nullptr, 0, st);   // E = f - MX (:130)
+    if (rc) return rc;
+    DCK(bp(2, MXE, n, (long long)plane, KE), "band product K~ E");               // :132
+    DCK(bp(3, KE, n, (long long)plane, MT), "band product m~^T KE");             // :192
+    return dense_pointwise_dispatch(h, n_chains, params, pitch, ll, grad, nullptr, MXE, KE, CX, MT, 1, st);
+}
+
 int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long pitch, double* ll, double* grad, cudaStream_t st) {
+    if (h->geom.HB <= kMaxHB && h->b < h->n - 1) return eval_band_products_dev(h, n_chains, params, pitch, ll, grad, st);
     const int n = h->n, D = h->D;
     const size_t nn = (size_t)n * n, plane = (size_t)n * n_chains;
     // dense (band-truncated) operators, rebuilt when the band tables change

@@ -199,10 +199,6 @@ __global__ void __launch_bounds__(32 * kFlowWarps, 1) flow_logpost_kernel(const 
         cp_async_wait_all();
         __syncthreads();                                     // X and the per-chain constants of this chain block are in place
         FLOW_DBG(tk1 = clock64());
-        if (a.stagger > 0) {                                 // de-phase the four warps of an SM sub-partition (see the launch code)
-            const long long t0 = clock64(), lim = (long long)(warp >> 2) * a.stagger;
-            while (clock64() - t0 < lim) { }
-        }
         auto dep_wait = [&](unsigned long long* bar) {
 #ifdef MAGI_FLOW_TIMELINE
             if (a.dbg) { const long long w0 = clock64(); mbar_wait(bar, par); dbg_t[2] += clock64() - w0; return; }

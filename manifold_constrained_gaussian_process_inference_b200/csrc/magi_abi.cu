@@ -35,9 +35,9 @@ extern "C" int magi_destroy(magi_handle* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) free_dev(h->d_band[i]);
     for (int i = 0; i < 7; ++i) free_dev(h->d_dense[i]);
-    free_dev(h->d_fragtab); free_dev(h->d_fragtab_nat); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
+    free_dev(h->d_fragtab); free_dev(h->d_fragtab_nat); free_dev(h->d_fragtab_bp); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
-    free_dev(h->d_dense_work); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
+    free_dev(h->d_dense_work); free_dev(h->d_dense_part); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
     free_dev(h->d_small); free_dev(h->d_flow_units); if (h->h_pin) cudaFreeHost(h->h_pin);
     hmc_free(h);
     comm_free(h);
@@ -245,12 +245,14 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
         for (int i = 0; i < 3; ++i) { f.beta[i] = h->beta[i]; f.inv_beta[i] = 1.0 / h->beta[i]; }
         const int grid = f.n_cblocks < h->sm_count ? f.n_cblocks : h->sm_count;
         f.dbg = nullptr;
-        { static const char* e = getenv("MAGI_FLOW_STAGGER"); f.stagger = e ? atoi(e) : 0; }
+#ifdef MAGI_DEV_KNOBS      // development builds only (tools/build_variant.py): per-warp phase clocks of the dataflow kernel
         static const bool dbg_flow = getenv("MAGI_DBG_CLOCKS") != nullptr;
         long long* d_dbgf = nullptr;
         if (dbg_flow) { cudaMalloc(&d_dbgf, sizeof(long long) * 16 * 16 * grid); cudaMemset(d_dbgf, 0, sizeof(long long) * 16 * 16 * grid); f.dbg = d_dbgf; }
+#endif
         CK(launch_flow_cfg(h->model, f, h->geom.HB, grid, h->flow_smem[fg], st), "flow_logpost_kernel launch");
         h->launches++;
+#ifdef MAGI_DEV_KNOBS
         if (dbg_flow) {
             cudaStreamSynchronize(st);
             std::vector<long long> v((size_t)16 * 16 * grid);
@@ -264,6 +266,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
                     s[6] / nw, s[7] / nw, s[8] / nw, s[9] / nw, s[10] / nw, s[11] / nw, s[12] / nw, s[13] / nw, s[14] / nw, s[15] / nw);
             cudaFree(d_dbgf);
         }
+#endif
         return MAGI_OK;
     }
     select_block_shape(h, n_chains);
@@ -276,14 +279,18 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     a.fragtab = h->d_fragtab; a.yobs = h->d_yobs; a.nobs = h->d_nobs; a.sigma_init = h->d_sigma_init;
     for (int i = 0; i < 3; ++i) { a.beta[i] = h->beta[i]; a.inv_beta[i] = 1.0 / h->beta[i]; }
     a.scratch = h->d_scratch;
-    { static const bool no_pp = getenv("MAGI_NO_PINGPONG") != nullptr; a.H = no_pp ? 1 : 0; }   // H != 0 disables the DMMA ping-pong (A/B measurement)
+    a.H = 0;
     a.dbg = nullptr;
+#ifdef MAGI_DEV_KNOBS      // development builds only: A/B switch of the DMMA ping-pong, per-warp phase clocks
+    { static const bool no_pp = getenv("MAGI_NO_PINGPONG") != nullptr; a.H = no_pp ? 1 : 0; }
     static const bool dbg_clocks = getenv("MAGI_DBG_CLOCKS") != nullptr;
     long long* d_dbg = nullptr;
     const int nblk = (n_chains + h->G * 8 - 1) / (h->G * 8), nwarp = h->G * h->DW;
     if (dbg_clocks) { cudaMalloc(&d_dbg, sizeof(long long) * 8 * nblk * nwarp); cudaMemset(d_dbg, 0, sizeof(long long) * 8 * nblk * nwarp); a.dbg = d_dbg; }
+#endif
     CK(launch_banded_cfg(h->model, a, h->geom.HB, h->DW, h->smem_bytes, st), "banded_logpost_kernel launch");
     h->launches++;
+#ifdef MAGI_DEV_KNOBS
     if (dbg_clocks) {
         cudaStreamSynchronize(st);
         std::vector<long long> v((size_t)8 * nblk * nwarp);
@@ -295,6 +302,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
                 nblk, nwarp, h->G, h->smem_bytes, s[0] / nw, s[1] / nw, s[2] / nw, s[3] / nw, s[4] / nw, s[5] / nw, s[7] / nw);
         cudaFree(d_dbg);
     }
+#endif
     return MAGI_OK;
 }
 
@@ -327,7 +335,9 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     // independent; other configurations take the single-stream path.
     const int chunk_min = 1024;
     int nchunks = n_chains / chunk_min; if (nchunks > 8) nchunks = 8;
+#ifdef MAGI_DEV_KNOBS
     { static const char* e = getenv("MAGI_E2E_CHUNKS"); if (e && atoi(e) > 0) nchunks = atoi(e); }
+#endif
     const int per = nchunks > 0 ? ((n_chains + nchunks - 1) / nchunks + 31) / 32 * 32 : n_chains;
     // the K1 variant is chosen by the size of the CALL, not of its chunks: how a batch is cut into chunks never changes the result
     struct DispatchPin { magi_handle* h; long long old; ~DispatchPin() { h->dispatch_chains = old; } } pin{h, h->dispatch_chains};
@@ -417,7 +427,7 @@ extern "C" int magi_set_band_tables(magi_handle* h, int dim, int which, const do
     const int t = which - MAGI_MAT_CINV_BAND;
     CK(cudaMemcpy(h->d_band[t] + (size_t)dim * tab, in, sizeof(double) * tab, cudaMemcpyHostToDevice), "H2D band table");
     h->band_set[(size_t)t * h->D + dim] = 1;
-    h->frag_dirty = true; h->frag_nat_dirty = true;
+    h->frag_dirty = true; h->frag_nat_dirty = true; h->frag_bp_dirty = true;
     h->dense_band_dirty = true;
     bool all = true;
     for (char c : h->band_set) all = all && c;

@@ -74,7 +74,7 @@ struct BandedArgs {
 
 // arguments of the dataflow K1 (flow_kernel.cuh)
 struct FlowArgs {
-    int n, P, n_chains, NP, RS0, n_units, n_cblocks, sigma_is_fixed, sigma_invalid, stagger, G;
+    int n, P, n_chains, NP, RS0, n_units, n_cblocks, sigma_is_fixed, sigma_invalid, G;
     long long pitch;
     const double* params;
     double* ll;

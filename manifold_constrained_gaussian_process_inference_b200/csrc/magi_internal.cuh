@@ -15,6 +15,8 @@ struct magi_handle {
     double* d_dense[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double* d_fragtab = nullptr;       // windowed kernel's layout
     double* d_fragtab_nat = nullptr;   // dataflow kernel's (natural) layout
+    double* d_fragtab_bp = nullptr;    // band-product route of many-component models: natural layout, 1/beta not folded in
+    bool frag_bp_dirty = true;
     double* d_yobs = nullptr;
     int* d_nobs = nullptr;
     double* d_sigma_init = nullptr;
@@ -32,6 +34,8 @@ struct magi_handle {
     // dense-mode work space
     double* d_dense_ops = nullptr;     // band-truncated dense Cinv~, mphi~, Kinv~ ([3][D][n x n]) for the dense path
     double* d_dense_work = nullptr;
+    double* d_dense_part = nullptr;    // [n_chains][D][4 + K] per-(chain, dimension) partial sums of the dense route's gradient stage
+    size_t dense_part_cap = 0;
     size_t dense_work_cap = 0;
     double* d_sk_work = nullptr;       // stream-K partial tiles and flags (gemm_f64.cuh)
     unsigned* d_sk_flags = nullptr;
@@ -72,5 +76,7 @@ void comm_free(magi_handle* h);
 int comm_allreduce_sum(magi_handle* h, double* buf, size_t n, cudaStream_t st);
 int comm_allgather(magi_handle* h, const double* send, double* recv, size_t n_per_rank, cudaStream_t st);
 cudaError_t launch_banded_cfg(int model, const BandedArgs& a, int HB, int DW, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_band_product(const double* fragtab, int view, const double* in, long long cs, long long ds, double* out, long long plane,
+                                int n, int b, int D, int n_chains, int sm_count, cudaStream_t st);
 cudaError_t launch_flow_cfg(int model, const FlowArgs& a, int HB, int grid, size_t smem_bytes, cudaStream_t st);
 }  // namespace magi

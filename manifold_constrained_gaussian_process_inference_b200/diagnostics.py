@@ -60,12 +60,6 @@ def ess_bulk(x) -> float:
     rho = 1.0 - (W - acov.mean(axis=1)) / var_plus
     rho[0] = 1.0
     # Geyer: sum of adjacent pairs, positive and monotone
-    t, tau = 1, -1.0
-    pairs = []
-    while t + 1 < n:
-        p = rho[t - 1] + rho[t] if t > 1 else rho[0] + rho[1]
-        pairs.append(p)
-        t += 2
     pairs = np.array([rho[2 * k] + rho[2 * k + 1] for k in range(n // 2)])
     pos = np.where(pairs < 0)[0]
     kmax = pos[0] if len(pos) else len(pairs)
