@@ -250,13 +250,20 @@ def section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, chains_to
         gbuf = torch.empty((world, ns_, nc_, ncol_), dtype=torch.float64, device=dev)
     e1.record()
     if world > 1:
-        full = Dm.allgather_draws_device(tg, stream=st, out=gbuf)
+        full = Dm.allgather_draws_device(tg, stream=st, out=gbuf)      # first gather into these buffers: pays NCCL's per-buffer set-up
+        ew0, ew1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ew0.record()
+        full = Dm.allgather_draws_device(tg, stream=st, out=gbuf)      # the same gather again, warm
+        ew1.record()
     else:
         full = Dm.device_draws_as_tensor(tg)
-    e2.record()
+        e2.record()
     torch.cuda.synchronize()
+    warm_gather_ms = ew0.elapsed_time(ew1) if world > 1 else 0.0
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), float(stt["grad_evals"])], dtype=torch.float64, device=dev)
+    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), float(stt["grad_evals"]), warm_gather_ms], dtype=torch.float64, device=dev)
     tmax, tsum = t.clone(), t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -265,12 +272,13 @@ def section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, chains_to
         d = full[:, :: max(1, full.shape[1] // 512)][:, :512].cpu().numpy()      # R-hat / ESS on 512 chains spread over all ranks' shards
         names = ["theta_a", "theta_b", "theta_c", "sigma_1", "sigma_2", "lp"]
         summ = pkg.diagnostics.summarize(d, names=names)
-        sample_s, gather_ms, evals = float(tmax[0]) * 1e-3, float(tmax[1]), float(tsum[2])
+        sample_s, gather_first_ms, evals, gather_ms = float(tmax[0]) * 1e-3, float(tmax[1]), float(tsum[2]), float(tmax[3])
         gathered_bytes = int(full.numel() * 8)
         res = {"config": {"workload": "fn201 cfg5: fn n=201 D=2 k=3 band=20, %d chains over %d GPU(s), HMC %d iterations (%d warm-up) x %d leapfrog steps" % (chains_total, world, iters, n_adapt, leapfrog),
                           "chains_total": chains_total, "chains_per_gpu": n_local, "scaling": "strong"},
                "metric": "leapfrog grad evals/sec (all chains)", "value": evals / sample_s, "unit": "evals/s", "n_gpus": world,
-               "sample_seconds": sample_s, "grad_evals": evals, "allgather_ms": gather_ms, "allgather_bytes": gathered_bytes,
+               "sample_seconds": sample_s, "grad_evals": evals, "allgather_ms": gather_ms, "allgather_first_call_ms": gather_first_ms,
+               "allgather_bytes": gathered_bytes,
                "allgather_GBps": (gathered_bytes / (gather_ms * 1e-3) * 1e-9) if world > 1 and gather_ms > 0 else None,
                "draws": list(full.shape), "accept_rate_median": float(np.median(stt["accept_rate"])),
                "posterior_mean": {nm: r["mean"] for nm, r in zip(names, summ)}, "rhat": {nm: r["rhat"] for nm, r in zip(names, summ)},
@@ -444,8 +452,12 @@ def main():
         if world > 1:
             dist.barrier()
         r5 = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, args.cfg5_chains, args.cfg5_iters)
+        # the same flow with a chain count that fills whole waves of the machine on 1, 2, 4 and 8 GPUs (a block of the banded kernel holds
+        # 32 chains, a wave 148 blocks: 8 x 2 x 4736 chains); 65 536 / 8 = 8192 chains per GPU are 1.73 waves, i.e. cost two
+        r5a = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, 8 * 2 * 148 * 32, max(40, args.cfg5_iters // 4))
         if rank == 0:
             extra["cfg5"] = r5
+            extra["cfg5_wave_aligned"] = r5a
     if rank == 0:
         value = world * chains * args.steps / (ms * 1e-3)
         per_launch_s = ms * 1e-3 / args.steps

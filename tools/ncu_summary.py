@@ -15,8 +15,6 @@ rows = list(csv.reader(open(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]; col = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
-half = len(data) // 2 if len(data) > 4000 else len(data)
-data = data[:half]
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = collections.Counter()
 for r in data:
