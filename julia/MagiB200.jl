@@ -116,4 +116,36 @@ function run_hmc_sampler(t::MagiTargetGPU, initial_params::Matrix{Float64}; n_sa
     return draws, acc, eps
 end
 
+"""
+Multi-GPU runs (one Julia process per GPU, chains sharded over the processes): rank 0 draws the NCCL unique id with
+`nccl_unique_id()`, the host distributes its 128 bytes (MPI.jl, a file, a socket), every rank calls `comm_init!`; the warm-up's
+pooled statistics and `allgather_draws!` then run inside the library on NVLink.  `out` is a device pointer to
+`world * n_stored * n_chains * n_cols` doubles (e.g. a CUDA.jl `CuArray`'s pointer; the library never touches CUDA.jl itself).
+"""
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    rc = ccall((:magi_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("magi_nccl_unique_id failed: " * last_error())
+    return id
+end
+function comm_init!(t::MagiTargetGPU, id::Vector{UInt8}, rank::Integer, world::Integer; n_chains_total::Integer)
+    rc = ccall((:magi_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), t.h, id, rank, world)
+    rc == 0 || error("magi_comm_init failed: " * last_error())
+    ccall((:magi_comm_warmup, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), t.h, C_NULL)
+    return n_chains_total          # pass it to magi_hmc_set_global after magi_hmc_init (run_hmc_sampler's chain_id_offset = first chain of this rank)
+end
+allgather_draws!(t::MagiTargetGPU, out::Ptr{Cdouble}) =
+    ccall((:magi_hmc_allgather_draws, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cvoid}), t.h, out, C_NULL) == 0 || error(last_error())
+
+"""`x_sampled` of solve_magi's result (src/MagiJl.jl:633-771): call `store_x!` after `magi_hmc_init` and before the kept iterations."""
+store_x!(t::MagiTargetGPU, n_chains_x::Integer, thin::Integer = 1) =
+    ccall((:magi_hmc_store_x, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), t.h, n_chains_x, thin) == 0 || error(last_error())
+function x_draws(t::MagiTargetGPU, n::Integer, D::Integer)
+    ns = Ref{Clonglong}(0); ncx = Ref{Cint}(0)
+    ccall((:magi_hmc_get_x_draws, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong, Ref{Clonglong}, Ref{Cint}), t.h, C_NULL, 0, ns, ncx)
+    out = Array{Float64}(undef, n, D, Int(ncx[]), Int(ns[]))          # [time, dimension, chain, draw]
+    ccall((:magi_hmc_get_x_draws, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong, Ref{Clonglong}, Ref{Cint}), t.h, out, ns[], ns, ncx)
+    return out
+end
+
 end # module
