@@ -168,6 +168,12 @@ int magi_comm_attach(magi_handle* h, void* nccl_comm, int rank, int world);
 int magi_comm_warmup(magi_handle* h, void* stream);
 int magi_hmc_allgather_draws(magi_handle* h, double* out_dev, void* stream);
 int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream);
+/* The same sampler with NUTS trajectories (multinomial sampling, generalised U-turn criterion; at most 2^max_depth - 1 leapfrog steps
+ * per transition) instead of static ones: the batched counterpart of run_nuts_sampler's kernel, Trajectory{MultinomialTS}(Leapfrog,
+ * GeneralisedNoUTurn) (src/samplers.jl:158-160).  All chains grow their trees in lock-step (doubling j = 2^j batched gradient evaluations);
+ * chains whose tree has stopped wait.  magi_nuts_get_stats: mean tree depth / leapfrog steps per transition of every chain. */
+int magi_nuts_run(magi_handle* h, int n_iter, int max_depth, int adapt, double target_accept, int store_draws, void* stream);
+int magi_nuts_get_stats(magi_handle* h, double* mean_depth /* n_chains */, double* mean_leapfrog /* n_chains */);
 int magi_hmc_reset_stats(magi_handle* h);
 int magi_hmc_get_state(magi_handle* h, double* params /* P x n_chains or NULL */, double* ll /* n_chains or NULL */);
 /* draws: [n_stored][n_chains][k + D + 1] = (theta, sigma, lp) like solve_magi's theta / sigma / lp (src/MagiJl.jl:633-771) */

@@ -47,7 +47,7 @@ EXPORTED = [
     "magi_launch_count", "magi_gp_covariances", "magi_gp_nlml_batched", "magi_hmc_init", "magi_hmc_run", "magi_hmc_reset_stats",
     "magi_hmc_get_state", "magi_hmc_get_draws", "magi_hmc_draws_dev", "magi_hmc_get_stats", "magi_hmc_grad_evals",
     "magi_hmc_set_global", "magi_setup_timing", "magi_nccl_unique_id", "magi_comm_init", "magi_comm_attach", "magi_comm_warmup",
-    "magi_hmc_allgather_draws", "magi_hmc_store_x", "magi_hmc_get_x_draws",
+    "magi_hmc_allgather_draws", "magi_hmc_store_x", "magi_hmc_get_x_draws", "magi_nuts_run", "magi_nuts_get_stats",
 ]
 
 
@@ -99,6 +99,8 @@ def _optional(L):
         L.magi_hmc_get_draws.argtypes = [vp, dp, ll, ctypes.POINTER(ll)]
         L.magi_hmc_draws_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ll), c_int_p, c_int_p]
         L.magi_hmc_get_stats.argtypes = [vp, dp, dp, c_int_p, dp, dp]
+        L.magi_nuts_run.argtypes = [vp, ci, ci, ci, ctypes.c_double, ci, vp]
+        L.magi_nuts_get_stats.argtypes = [vp, dp, dp]
         L.magi_hmc_store_x.argtypes = [vp, ci, ci]
         L.magi_hmc_get_x_draws.argtypes = [vp, dp, ll, ctypes.POINTER(ll), c_int_p]
         L.magi_hmc_grad_evals.argtypes = [vp]

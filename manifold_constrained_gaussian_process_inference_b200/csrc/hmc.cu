@@ -41,7 +41,18 @@ struct HmcState {
     double *xdraws = nullptr; long long xdraws_cap = 0, n_xdraws = 0;
     int x_chains = 0, x_thin = 1;
     long long acc_count = 0;
+    // ---- batched NUTS (magi_nuts_run): per-chain tree state; allocated at the first NUTS run ----
+    double *ql = nullptr, *pl = nullptr, *gl = nullptr, *qr = nullptr, *pr = nullptr, *gr = nullptr;   // end points of the tree
+    double *qprop = nullptr, *gprop = nullptr, *llprop = nullptr;      // multinomial sample of the whole tree
+    double *qsub = nullptr, *gsub = nullptr, *llsub = nullptr;         // ... of the subtree being built
+    double *rho = nullptr, *srho = nullptr;                            // sums of the momenta: tree, subtree
+    double *pck = nullptr, *rck = nullptr;                             // [max_depth][n_chains][P] checkpoints (momentum, cumulative sum)
+    double *lsw = nullptr, *slsw = nullptr, *sum_acc = nullptr;        // log sum of weights: tree, subtree; sum of min(1, exp(-dH))
+    int *tflags = nullptr, *tdir = nullptr, *nleap = nullptr, *tdepth = nullptr, *n_active = nullptr;
+    long long *depth_sum = nullptr, *leap_sum = nullptr;               // statistics over the iterations since magi_hmc_reset_stats
+    int nuts_max_depth = 0;
 };
+constexpr int kTreeDone = 1, kTreeSubInvalid = 2, kTreeDiverged = 4;
 
 // ---- Philox4x32-10 counter RNG ----
 __device__ __forceinline__ void philox4x32(unsigned int c[4], unsigned int k0, unsigned int k1) {
@@ -141,6 +152,7 @@ struct HmcFinish {
     int adapt, store, n_draw_cols, nD, K, D, sigma_is_fixed;
     double delta, mu_scale;
     int accumulate_window, accumulate_x, store_x;
+    int nuts;            // 1: the transition was a NUTS tree (state, acceptance statistic and divergence come from the tree)
 };
 
 // last half kick, Hamiltonian, accept/reject, dual averaging, draw storage (one block per chain)
@@ -151,31 +163,44 @@ __global__ void __launch_bounds__(256) hmc_finish_kernel(HmcState s, int P, HmcF
     const size_t base = (size_t)c * P;
     const double eps = s.eps[c];
     double kin = 0.0;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const double p = s.p[base + i] + 0.5 * eps * s.g[base + i];
-        kin += 0.5 * p * p * s.minv[i];
+    if (f.nuts) {                                   // the tree's multinomial sample becomes the state
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { s.q[base + i] = s.qprop[base + i]; s.g[base + i] = s.gprop[base + i]; }
+    } else {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const double p = s.p[base + i] + 0.5 * eps * s.g[base + i];
+            kin += 0.5 * p * p * s.minv[i];
+        }
     }
     for (int o = 16; o > 0; o >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = kin;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double k1 = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) k1 += sh[i];
-        const double h1 = -s.ll[c] + k1;
-        double a = exp(s.h0[c] - h1);
-        const bool divergent = !isfinite(h1) || !isfinite(a) && !(s.h0[c] - h1 > 0);
-        if (!isfinite(h1)) a = 0.0;
-        if (a > 1.0 || (isinf(a) && s.h0[c] - h1 > 0)) a = 1.0;
-        if (isnan(a)) a = 0.0;
-        double z0, z1;
-        normal_pair(s.seed, c + s.chain_offset, s.iter, 0u, 1u, z0, z1);
-        unsigned int cc[4] = {1u, 2u, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};     // stream 2: the accept uniform
-        const unsigned long long key = chain_key(s.seed, c + s.chain_offset);
-        philox4x32(cc, (unsigned int)key, (unsigned int)(key >> 32));
-        const double u = u01(cc[0], cc[1]);
-        s_accept = (u < a) ? 1 : 0;
+        double a;
+        bool count_div;
+        if (f.nuts) {
+            s.ll[c] = s.llprop[c];
+            a = s.nleap[c] > 0 ? s.sum_acc[c] / s.nleap[c] : 0.0;          // acceptance statistic of the tree (Stan / AdvancedHMC)
+            count_div = (s.tflags[c] & kTreeDiverged) != 0;
+            s_accept = 1;
+            s.depth_sum[c] += s.tdepth[c]; s.leap_sum[c] += s.nleap[c];
+        } else {
+            double k1 = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) k1 += sh[i];
+            const double h1 = -s.ll[c] + k1;
+            a = exp(s.h0[c] - h1);
+            const bool divergent = !isfinite(h1) || !isfinite(a) && !(s.h0[c] - h1 > 0);
+            if (!isfinite(h1)) a = 0.0;
+            if (a > 1.0 || (isinf(a) && s.h0[c] - h1 > 0)) a = 1.0;
+            if (isnan(a)) a = 0.0;
+            unsigned int cc[4] = {1u, 2u, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};     // stream 2: the accept uniform
+            const unsigned long long key = chain_key(s.seed, c + s.chain_offset);
+            philox4x32(cc, (unsigned int)key, (unsigned int)(key >> 32));
+            const double u = u01(cc[0], cc[1]);
+            s_accept = (u < a) ? 1 : 0;
+            count_div = divergent || (s.h0[c] - h1) < -1000.0;
+        }
         s.acc_sum[c] += a;
-        if (divergent || (s.h0[c] - h1) < -1000.0) s.n_div[c] += 1;
+        if (count_div) s.n_div[c] += 1;
         if (f.adapt) {
             // Nesterov dual averaging (Hoffman & Gelman 2014; AdvancedHMC/Stan defaults)
             double* da = s.da + (size_t)c * 5;     // m, Hbar, log_eps_bar, mu, (unused)
@@ -273,11 +298,200 @@ __global__ void fill_double_kernel(double* p, size_t nel, double v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nel; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Batched NUTS (run_nuts_sampler's trajectory, src/samplers.jl:158-160: Trajectory{MultinomialTS}(Leapfrog, GeneralisedNoUTurn)).
+// AdvancedHMC is not under the reference tree: the transition is restated from its published algorithm (Hoffman & Gelman
+// 2014; Betancourt 2017) in the ITERATIVE form (no recursion: a subtree of 2^j leaves is built leaf by leaf, the U-turn
+// checks inside it use O(depth) checkpoints of (momentum, cumulative momentum sum) addressed by the bits of the leaf index;
+// Phan, Pradhan, Jankowiak 2019).  All chains grow their trees in lock-step -- depth j costs 2^j batched gradient
+// evaluations for every chain still growing; a chain whose tree has stopped is masked and waits -- so one chain never
+// changes another chain's result and the draws do not depend on how the chains are sharded.
+// Per-chain random numbers: Philox counter words (kind, index, iteration): 3 = direction of doubling `index`, 4 = multinomial
+// choice at leaf `index` of the transition, 5 = choice between the old tree and the new subtree at doubling `index`.
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double chain_uniform(const HmcState& s, long long c, unsigned int kind, unsigned int index) {
+    unsigned int cc[4] = {kind, index, (unsigned int)s.iter, (unsigned int)(s.iter >> 32)};
+    const unsigned long long key = chain_key(s.seed, c + s.chain_offset);
+    philox4x32(cc, (unsigned int)key, (unsigned int)(key >> 32));
+    return u01(cc[0], cc[1]);
+}
+__device__ __forceinline__ double log_add_exp(double a, double b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    const double m = fmax(a, b);
+    return m + log(exp(a - m) + exp(b - m));
+}
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {      // ordered: bit-reproducible
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+    return r;
+}
+
+// momentum refresh, H0, a tree of one node (the current state), direction of the first doubling
+__global__ void __launch_bounds__(256) nuts_begin_kernel(HmcState s, int P) {
+    __shared__ double sh[8];
+    const long long c = blockIdx.x;
+    const size_t base = (size_t)c * P;
+    double kin = 0.0;
+    for (int i2 = threadIdx.x; 2 * i2 < P; i2 += blockDim.x) {
+        double z[2];
+        normal_pair(s.seed, c + s.chain_offset, s.iter, (unsigned int)i2, 0u, z[0], z[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = 2 * i2 + u;
+            if (i < P) {
+                const double mi = s.minv[i], p = z[u] * rsqrt(mi), q = s.q[base + i], g = s.g[base + i];
+                kin += 0.5 * p * p * mi;
+                s.p[base + i] = p;
+                s.ql[base + i] = q; s.qr[base + i] = q; s.qprop[base + i] = q;
+                s.pl[base + i] = p; s.pr[base + i] = p; s.rho[base + i] = p;
+                s.gl[base + i] = g; s.gr[base + i] = g; s.gprop[base + i] = g;
+                s.srho[base + i] = 0.0;
+            }
+        }
+    }
+    kin = block_sum_256(kin, sh);
+    if (threadIdx.x == 0) {
+        s.h0[c] = -s.ll[c] + kin;
+        s.llprop[c] = s.ll[c];
+        s.lsw[c] = 0.0; s.slsw[c] = -INFINITY; s.sum_acc[c] = 0.0;
+        s.nleap[c] = 0; s.tdepth[c] = 0; s.tflags[c] = 0;
+        s.tdir[c] = chain_uniform(s, c, 3u, 0u) < 0.5 ? 1 : -1;
+    }
+}
+
+// first half of a leapfrog step of the moving state of every chain whose subtree is still growing
+__global__ void nuts_pre_kernel(HmcState s, int P) {
+    const long long c = blockIdx.x;
+    if (s.tflags[c] & (kTreeDone | kTreeSubInvalid)) return;
+    const double eps = s.tdir[c] * s.eps[c];
+    const size_t base = (size_t)c * P;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < P; i += gridDim.y * blockDim.x) {
+        const double p = s.p[base + i] + 0.5 * eps * s.g[base + i];
+        s.p[base + i] = p;
+        s.q[base + i] += eps * s.minv[i] * p;
+    }
+}
+
+// second half kick of leaf `leaf` of the current doubling; energy error, multinomial choice inside the subtree, checkpoints
+// and U-turn checks inside the subtree
+__global__ void __launch_bounds__(256) nuts_post_kernel(HmcState s, int P, int leaf) {
+    __shared__ double sh[8];
+    __shared__ int s_take;
+    const long long c = blockIdx.x;
+    if (s.tflags[c] & (kTreeDone | kTreeSubInvalid)) return;
+    const size_t base = (size_t)c * P, NP = (size_t)s.n_chains * P;
+    const double eps = s.tdir[c] * s.eps[c];
+    double kin = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double p = s.p[base + i] + 0.5 * eps * s.g[base + i];
+        s.p[base + i] = p;
+        s.srho[base + i] += p;
+        kin += 0.5 * p * p * s.minv[i];
+    }
+    kin = block_sum_256(kin, sh);
+    if (threadIdx.x == 0) {
+        double dh = (-s.ll[c] + kin) - s.h0[c];
+        if (!isfinite(dh)) dh = INFINITY;
+        const double w = -dh;
+        s.sum_acc[c] += dh <= 0.0 ? 1.0 : exp(-dh);
+        const int nl = s.nleap[c] + 1;
+        s.nleap[c] = nl;
+        const double nw = log_add_exp(s.slsw[c], w);
+        s_take = (w > -INFINITY && log(chain_uniform(s, c, 4u, (unsigned int)nl)) < w - nw) ? 1 : 0;     // uniform over the subtree's leaves by weight
+        s.slsw[c] = nw;
+        if (dh > 1000.0) s.tflags[c] |= kTreeDiverged | kTreeSubInvalid;
+    }
+    __syncthreads();
+    if (s_take) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { s.qsub[base + i] = s.q[base + i]; s.gsub[base + i] = s.g[base + i]; }
+        if (threadIdx.x == 0) s.llsub[c] = s.ll[c];
+    }
+    const int idx_max = __popc(leaf >> 1);
+    if ((leaf & 1) == 0) {                              // even leaf: becomes the checkpoint of its level
+        double* pk = s.pck + (size_t)idx_max * NP + base;
+        double* rk = s.rck + (size_t)idx_max * NP + base;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { pk[i] = s.p[base + i]; rk[i] = s.srho[base + i]; }
+    } else {                                            // odd leaf: closes `ntrail` nested subtrees; U-turn check of each
+        const int ntrail = __ffs(~leaf) - 1;            // number of trailing one bits
+        bool turning = false;
+        for (int k = idx_max; k >= idx_max - ntrail + 1; --k) {
+            const double* pk = s.pck + (size_t)k * NP + base;
+            const double* rk = s.rck + (size_t)k * NP + base;
+            double a = 0.0, b = 0.0;
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const double r = s.srho[base + i] - rk[i] + pk[i];          // momentum sum of the nested subtree
+                a += s.minv[i] * pk[i] * r;
+                b += s.minv[i] * s.p[base + i] * r;
+            }
+            a = block_sum_256(a, sh); b = block_sum_256(b, sh);
+            turning |= (a <= 0.0) || (b <= 0.0);
+        }
+        if (threadIdx.x == 0 && turning) s.tflags[c] |= kTreeSubInvalid;
+    }
+}
+
+// end of doubling `depth`: merge the subtree into the tree (biased progressive sampling), U-turn check of the whole tree,
+// next direction; chains that go on are counted in *n_active
+__global__ void __launch_bounds__(256) nuts_merge_kernel(HmcState s, int P, int depth, int max_depth) {
+    __shared__ double sh[8];
+    __shared__ int s_acc, s_dir;
+    const long long c = blockIdx.x;
+    int fl = s.tflags[c];
+    if (fl & kTreeDone) return;
+    if (fl & kTreeSubInvalid) { if (threadIdx.x == 0) s.tflags[c] = fl | kTreeDone; return; }     // the subtree is discarded
+    const size_t base = (size_t)c * P;
+    const int v = s.tdir[c];
+    if (threadIdx.x == 0) s_acc = log(chain_uniform(s, c, 5u, (unsigned int)depth)) < s.slsw[c] - s.lsw[c] ? 1 : 0;
+    __syncthreads();
+    double* qe = v > 0 ? s.qr : s.ql; double* pe = v > 0 ? s.pr : s.pl; double* ge = v > 0 ? s.gr : s.gl;
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        if (s_acc) { s.qprop[base + i] = s.qsub[base + i]; s.gprop[base + i] = s.gsub[base + i]; }
+        qe[base + i] = s.q[base + i]; pe[base + i] = s.p[base + i]; ge[base + i] = s.g[base + i];      // the moving state is the new end point
+        const double r = s.rho[base + i] + s.srho[base + i];
+        s.rho[base + i] = r;
+        s.srho[base + i] = 0.0;
+        a += s.minv[i] * s.pl[base + i] * r;
+        b += s.minv[i] * s.pr[base + i] * r;
+    }
+    a = block_sum_256(a, sh); b = block_sum_256(b, sh);
+    if (threadIdx.x == 0) {
+        if (s_acc) s.llprop[c] = s.llsub[c];
+        s.lsw[c] = log_add_exp(s.lsw[c], s.slsw[c]);
+        s.slsw[c] = -INFINITY;
+        s.tdepth[c] = depth + 1;
+        if (a <= 0.0 || b <= 0.0 || depth + 1 >= max_depth) { s.tflags[c] = fl | kTreeDone; s_dir = 0; }
+        else {
+            s_dir = chain_uniform(s, c, 3u, (unsigned int)(depth + 1)) < 0.5 ? 1 : -1;
+            s.tdir[c] = s_dir;
+            atomicAdd(s.n_active, 1);
+        }
+    }
+    __syncthreads();
+    if (s_dir != 0) {                                   // the next subtree starts from the end point in the new direction
+        const double* qs = s_dir > 0 ? s.qr : s.ql; const double* ps = s_dir > 0 ? s.pr : s.pl; const double* gs = s_dir > 0 ? s.gr : s.gl;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { s.q[base + i] = qs[base + i]; s.p[base + i] = ps[base + i]; s.g[base + i] = gs[base + i]; }
+    }
+}
+
 void hmc_free(magi_handle* h) {
     HmcState* s = (HmcState*)h->hmc;
     if (!s) return;
     double* ptrs[] = {s->q, s->p, s->g, s->ll, s->q0, s->g0, s->ll0, s->h0, s->minv, s->eps, s->da, s->acc_sum, s->wsum, s->wsq, s->wpart, s->draws, s->xsum, s->xdraws};
     for (double* p : ptrs) if (p) cudaFree(p);
+    double* tree[] = {s->ql, s->pl, s->gl, s->qr, s->pr, s->gr, s->qprop, s->gprop, s->llprop, s->qsub, s->gsub, s->llsub, s->rho, s->srho, s->pck, s->rck,
+                      s->lsw, s->slsw, s->sum_acc};
+    for (double* p : tree) if (p) cudaFree(p);
+    int* ti[] = {s->tflags, s->tdir, s->nleap, s->tdepth, s->n_active};
+    for (int* p : ti) if (p) cudaFree(p);
+    if (s->depth_sum) cudaFree(s->depth_sum);
+    if (s->leap_sum) cudaFree(s->leap_sum);
     if (s->n_div) cudaFree(s->n_div);
     delete s;
     h->hmc = nullptr;
@@ -343,12 +557,41 @@ extern "C" int magi_hmc_set_global(magi_handle* h, long long n_chains_total, int
 
 // Runs n_iter transitions of n_leapfrog steps.  adapt != 0: warm-up (dual averaging towards target_accept and windowed
 // metric adaptation over these n_iter iterations).  store_draws != 0: appends (theta, sigma, lp) of every chain per iteration.
-extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream_) {
-    if (!h || !h->hmc || n_iter < 0 || n_leapfrog < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_run: bad argument (call magi_hmc_init first)");
+// tree state of the batched NUTS, allocated at the first run (or when a deeper tree is asked for)
+static int nuts_alloc(magi_handle* h, HmcState* s, int max_depth) {
+    const size_t NP = (size_t)s->n_chains * s->P, nc = (size_t)s->n_chains;
+    if (!s->ql) {
+        double** big[] = {&s->ql, &s->pl, &s->gl, &s->qr, &s->pr, &s->gr, &s->qprop, &s->gprop, &s->qsub, &s->gsub, &s->rho, &s->srho};
+        for (double** b : big) HCK(cudaMalloc(b, sizeof(double) * NP), "cudaMalloc NUTS tree state");
+        double** small[] = {&s->llprop, &s->llsub, &s->lsw, &s->slsw, &s->sum_acc};
+        for (double** b : small) HCK(cudaMalloc(b, sizeof(double) * nc), "cudaMalloc NUTS per-chain");
+        int** si[] = {&s->tflags, &s->tdir, &s->nleap, &s->tdepth};
+        for (int** b : si) HCK(cudaMalloc(b, sizeof(int) * nc), "cudaMalloc NUTS per-chain");
+        HCK(cudaMalloc(&s->n_active, sizeof(int)), "cudaMalloc");
+        HCK(cudaMalloc(&s->depth_sum, sizeof(long long) * nc), "cudaMalloc");
+        HCK(cudaMalloc(&s->leap_sum, sizeof(long long) * nc), "cudaMalloc");
+        HCK(cudaMemset(s->depth_sum, 0, sizeof(long long) * nc), "memset");
+        HCK(cudaMemset(s->leap_sum, 0, sizeof(long long) * nc), "memset");
+    }
+    if (max_depth > s->nuts_max_depth) {
+        if (s->pck) cudaFree(s->pck);
+        if (s->rck) cudaFree(s->rck);
+        s->pck = s->rck = nullptr;
+        HCK(cudaMalloc(&s->pck, sizeof(double) * NP * max_depth), "cudaMalloc NUTS checkpoints");
+        HCK(cudaMalloc(&s->rck, sizeof(double) * NP * max_depth), "cudaMalloc NUTS checkpoints");
+        s->nuts_max_depth = max_depth;
+    }
+    (void)h;
+    return MAGI_OK;
+}
+
+// n_leapfrog >= 1, max_depth = 0: static trajectories; max_depth >= 1: NUTS trees of at most 2^max_depth - 1 leapfrog steps
+static int hmc_run_impl(magi_handle* h, int n_iter, int n_leapfrog, int max_depth, int adapt, double target_accept, int store_draws, void* stream_) {
     HCK(cudaSetDevice(h->device), "cudaSetDevice");
     HmcState* s = (HmcState*)h->hmc;
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : h->stream;
     const int P = s->P, nc = s->n_chains;
+    if (max_depth > 0) { int rc = nuts_alloc(h, s, max_depth); if (rc) return rc; }
     if (store_draws) {
         const long long need = s->n_draws + n_iter;
         if (need > s->draws_cap) {
@@ -379,7 +622,29 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
     f.delta = target_accept; f.mu_scale = 10.0;
     h->dispatch_chains = s->n_chains_total > 0 ? s->n_chains_total : 0;      // the same K1 variant on every rank of a sharded run
     struct DispatchReset { magi_handle* h; ~DispatchReset() { h->dispatch_chains = 0; } } dispatch_reset{h};
+    f.nuts = max_depth > 0 ? 1 : 0;
     for (int it = 0; it < n_iter; ++it) {
+        if (max_depth > 0) {
+            nuts_begin_kernel<<<nc, 256, 0, st>>>(*s, P);
+            h->launches++;
+            for (int depth = 0; depth < max_depth; ++depth) {
+                HCK(cudaMemsetAsync(s->n_active, 0, sizeof(int), st), "memset");
+                for (int leaf = 0; leaf < (1 << depth); ++leaf) {
+                    nuts_pre_kernel<<<egrid, 256, 0, st>>>(*s, P);
+                    int rc = eval_dev(h, nc, s->q, P, s->ll, s->g, st);
+                    if (rc) return rc;
+                    s->grad_evals += nc;                     // (masked chains included: the batch is evaluated as a whole)
+                    nuts_post_kernel<<<nc, 256, 0, st>>>(*s, P, leaf);
+                    h->launches += 2;
+                }
+                nuts_merge_kernel<<<nc, 256, 0, st>>>(*s, P, depth, max_depth);
+                h->launches++;
+                int active = 0;
+                HCK(cudaMemcpyAsync(&active, s->n_active, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H active chains");
+                HCK(cudaStreamSynchronize(st), "nuts sync");
+                if (active == 0) break;
+            }
+        } else {
         hmc_prep_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s);
         hmc_begin_kernel<<<dim3(nc, 1), 256, 0, st>>>(*s, P);      // one block per chain (ordered reduction of the kinetic energy)
         h->launches += 2;
@@ -388,6 +653,7 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
             if (rc) return rc;
             s->grad_evals += nc;
             if (l + 1 < n_leapfrog) { hmc_kick_drift_kernel<<<egrid, 256, 0, st>>>(*s, P); h->launches++; }
+        }
         }
         const bool in_slow = adapt && it >= init_buf && it < n_iter - term_buf;
         f.store = store_draws; f.accumulate_window = in_slow ? 1 : 0; f.accumulate_x = store_draws ? 1 : 0;
@@ -430,6 +696,32 @@ extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adap
     if (adapt && n_iter > 0) { hmc_restart_da_kernel<<<(nc + 255) / 256, 256, 0, st>>>(*s, 1); h->launches++; }
     HCK(cudaGetLastError(), "hmc kernels");
     HCK(cudaStreamSynchronize(st), "hmc sync");
+    return MAGI_OK;
+}
+
+extern "C" int magi_hmc_run(magi_handle* h, int n_iter, int n_leapfrog, int adapt, double target_accept, int store_draws, void* stream_) {
+    if (!h || !h->hmc || n_iter < 0 || n_leapfrog < 1) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_hmc_run: bad argument (call magi_hmc_init first)");
+    return hmc_run_impl(h, n_iter, n_leapfrog, 0, adapt, target_accept, store_draws, stream_);
+}
+
+// The same sampler with NUTS trajectories (multinomial sampling, generalised U-turn criterion) of at most 2^max_depth - 1
+// leapfrog steps instead of static ones: the batched counterpart of run_nuts_sampler's kernel (src/samplers.jl:158-160).
+extern "C" int magi_nuts_run(magi_handle* h, int n_iter, int max_depth, int adapt, double target_accept, int store_draws, void* stream_) {
+    if (!h || !h->hmc || n_iter < 0 || max_depth < 1 || max_depth > 12) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_nuts_run: bad argument (call magi_hmc_init first; 1 <= max_depth <= 12)");
+    return hmc_run_impl(h, n_iter, 1, max_depth, adapt, target_accept, store_draws, stream_);
+}
+
+// mean tree depth and mean number of leapfrog steps per transition of every chain since magi_hmc_reset_stats (NUTS runs)
+extern "C" int magi_nuts_get_stats(magi_handle* h, double* mean_depth, double* mean_leapfrog) {
+    if (!h || !h->hmc) return set_error(MAGI_ERR_INVALID_ARGUMENT, "magi_nuts_get_stats: no sampler state");
+    HmcState* s = (HmcState*)h->hmc;
+    if (!s->depth_sum) return set_error(MAGI_ERR_NOT_READY, "magi_nuts_get_stats: no NUTS run yet");
+    HCK(cudaSetDevice(h->device), "cudaSetDevice");
+    std::vector<long long> a(s->n_chains), b(s->n_chains);
+    HCK(cudaMemcpy(a.data(), s->depth_sum, sizeof(long long) * s->n_chains, cudaMemcpyDeviceToHost), "D2H");
+    HCK(cudaMemcpy(b.data(), s->leap_sum, sizeof(long long) * s->n_chains, cudaMemcpyDeviceToHost), "D2H");
+    const double cnt = s->acc_count > 0 ? (double)s->acc_count : 1.0;
+    for (int c = 0; c < s->n_chains; ++c) { if (mean_depth) mean_depth[c] = a[c] / cnt; if (mean_leapfrog) mean_leapfrog[c] = b[c] / cnt; }
     return MAGI_OK;
 }
 
@@ -540,5 +832,6 @@ extern "C" int magi_hmc_reset_stats(magi_handle* h) {
     HCK(cudaMemset(s->n_div, 0, sizeof(int) * s->n_chains), "memset");
     HCK(cudaMemset(s->xsum, 0, sizeof(double) * (size_t)s->n_chains * h->n * h->D), "memset");
     s->acc_count = 0; s->n_draws = 0; s->xsum_count = 0; s->n_xdraws = 0;
+    if (s->depth_sum) { HCK(cudaMemset(s->depth_sum, 0, sizeof(long long) * s->n_chains), "memset"); HCK(cudaMemset(s->leap_sum, 0, sizeof(long long) * s->n_chains), "memset"); }
     return MAGI_OK;
 }

@@ -17,7 +17,7 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
                     target_accept_ratio: float = 0.8, initial_step_size: float = 0.1, n_leapfrog: int = 20,
                     seed: int = 0, chain_id_offset: int = 0, keep_on_device: bool = False,
                     n_chains_total: int | None = None, window_allreduce=None, stream: int = 0,
-                    x_chains: int = 0, x_thin: int = 1):
+                    x_chains: int = 0, x_thin: int = 1, max_tree_depth: int = 0):
     """Argument meaning follows ``run_nuts_sampler``: ``n_samples`` is the TOTAL number of iterations including the
     ``n_adapts`` warm-up iterations, which are dropped (``drop_warmup=true``).  ``initial_params`` is (n_chains, P).
 
@@ -27,6 +27,10 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
     (shards aligned to ``n_chains_total / 64`` chains).  ``window_allreduce`` (``distributed.make_window_allreduce``) is the
     host-callback alternative for transports other than NCCL.  ``stream``: CUDA stream handle the sampler runs on (0: the
     handle's own stream).
+
+    ``max_tree_depth`` > 0 replaces the static trajectories by batched NUTS trees (multinomial sampling, generalised U-turn
+    criterion: the reference's ``Trajectory{MultinomialTS}(Leapfrog, GeneralisedNoUTurn)``, src/samplers.jl:158-160) of at most
+    ``2**max_tree_depth - 1`` leapfrog steps; ``n_leapfrog`` is then ignored and ``stats`` gains ``tree_depth`` / ``n_leapfrog_mean``.
 
     ``x_chains`` > 0 keeps the latent trajectories X of the first ``x_chains`` chains at every ``x_thin``-th kept iteration
     (``stats["x_sampled"]``, shape (n_stored, x_chains, n, D): the reference's ``x_sampled`` S×n×D per chain).
@@ -47,14 +51,19 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
         cb = window_allreduce if window_allreduce is not None else ctypes.cast(None, _lib.ALLREDUCE_FN)
         target._window_allreduce = cb                      # keep the ctypes callback alive as long as the handle
         _lib.check(L.magi_hmc_set_global(h, ctypes.c_longlong(int(n_chains_total if n_chains_total is not None else nc + chain_id_offset)), cb, None))
+    stp = ctypes.c_void_p(stream) if stream else None
+    if max_tree_depth > 0:
+        run = lambda n_it, adapt, store: L.magi_nuts_run(h, int(n_it), int(max_tree_depth), adapt, float(target_accept_ratio), store, stp)
+    else:
+        run = lambda n_it, adapt, store: L.magi_hmc_run(h, int(n_it), int(n_leapfrog), adapt, float(target_accept_ratio), store, stp)
     if n_adapts > 0:
-        _lib.check(L.magi_hmc_run(h, int(n_adapts), int(n_leapfrog), 1, float(target_accept_ratio), 0, ctypes.c_void_p(stream) if stream else None))
+        _lib.check(run(n_adapts, 1, 0))
     _lib.check(L.magi_hmc_reset_stats(h))
     if x_chains > 0:
         _lib.check(L.magi_hmc_store_x(h, int(x_chains), int(x_thin)))
     n_keep = int(n_samples) - int(n_adapts)
     if n_keep > 0:
-        _lib.check(L.magi_hmc_run(h, n_keep, int(n_leapfrog), 0, float(target_accept_ratio), 1, ctypes.c_void_p(stream) if stream else None))
+        _lib.check(run(n_keep, 0, 1))
     ncols = target.n_params_ode + target.n_dims + 1
     chain = None
     if not keep_on_device:
@@ -66,6 +75,10 @@ def run_hmc_sampler(target: MagiTarget, initial_params, n_samples: int = 2000, n
     _lib.check(L.magi_hmc_get_stats(h, _lib.as_dp(acc), _lib.as_dp(eps), ndiv.ctypes.data_as(_lib.c_int_p), _lib.as_dp(xmean), _lib.as_dp(minv)))
     stats = dict(accept_rate=acc, step_size=eps, n_divergent=ndiv, x_mean=xmean, inverse_metric=minv,
                  grad_evals=int(L.magi_hmc_grad_evals(h)), n_leapfrog=int(n_leapfrog))
+    if max_tree_depth > 0:
+        td, nl = np.empty(nc), np.empty(nc)
+        _lib.check(L.magi_nuts_get_stats(h, _lib.as_dp(td), _lib.as_dp(nl)))
+        stats["tree_depth"], stats["n_leapfrog_mean"] = td, nl
     if x_chains > 0:
         ns, ncx = ctypes.c_longlong(), ctypes.c_int()
         _lib.check(L.magi_hmc_get_x_draws(h, None, ctypes.c_longlong(0), ctypes.byref(ns), ctypes.byref(ncx)))

@@ -5,7 +5,7 @@ Kept from the reference: the config keys and defaults (:kernel "matern52", :nite
 :thetaInit; :208-220), ``sigma_is_fixed = :sigma and :phi both given`` (:224), linear-interpolation X init (:351-410),
 bounds-based θ init (:412-453), band clamp (:459), parameter vector layout [vec(X); θ; log σ] (:526-569), burn-in split
 (:578-581) and the shape of the result (θ, x_sampled, σ, φ, lp; :633-771).  New keys: :nChains (independent chains, default 1024),
-:nLeapfrog (static trajectory length), :setupMode, :seed, :device, :xChains (chains whose latent trajectories are kept, default
+:nLeapfrog (static trajectory length), :maxTreeDepth (> 0: batched NUTS trees instead, the reference's sampler), :setupMode, :seed, :device, :xChains (chains whose latent trajectories are kept, default
 min(nChains, 16)), :xThin (keep X at every xThin-th kept iteration, default 1).
 
 When ``config['phi']`` and/or ``config['sigma']`` are absent they are estimated per dimension by minimising the GP negative log
@@ -148,7 +148,7 @@ def solve_magi(y_obs, t_obs, ode_system: OdeSystem, config=None, initial_params=
     x_chains = int(get("xChains", min(n_chains, 16)))
     chain, stats = run_hmc_sampler(target, p0, n_samples=niter, n_adapts=n_adapts, target_accept_ratio=delta,
                                    initial_step_size=eps0, n_leapfrog=n_leap, seed=int(get("seed", 0)),
-                                   x_chains=x_chains, x_thin=int(get("xThin", 1)))
+                                   x_chains=x_chains, x_thin=int(get("xThin", 1)), max_tree_depth=int(get("maxTreeDepth", 0)))
     theta = chain[:, :, :k]
     sig = chain[:, :, k:k + D]
     if sigma_is_fixed:
