@@ -454,7 +454,7 @@ def main():
         r5 = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, args.cfg5_chains, args.cfg5_iters)
         # the same flow with a chain count that fills whole waves of the machine on 1, 2, 4 and 8 GPUs (a block of the banded kernel holds
         # 32 chains, a wave 148 blocks: 8 x 2 x 4736 chains); 65 536 / 8 = 8192 chains per GPU are 1.73 waves, i.e. cost two
-        r5a = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, 8 * 2 * 148 * 32, max(40, args.cfg5_iters // 4))
+        r5a = section_cfg5(pkg, synthetic, torch, dist, dev, local, rank, world, 8 * 2 * 148 * 32, args.cfg5_iters)
         if rank == 0:
             extra["cfg5"] = r5
             extra["cfg5_wave_aligned"] = r5a

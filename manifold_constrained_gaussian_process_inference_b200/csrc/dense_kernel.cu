@@ -388,8 +388,19 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         return e;
     };
     // X_d(i, c) = params[c * pitch + d * n + i]
-    DCK(gemm(Mphi, false, params, 1, pitch, n, MXE), "dense gemm m~ X");
-    DCK(gemm(Cinv, false, params, 1, pitch, n, CX), "dense gemm C~ X");
+    {   // MX = m~ X and CX = C~ X in ONE launch (2 D batched products sharing the B operand X: batch z = d + D * which):
+        // 4 D instead of 2 x 2 D tile rows for the persistent stream-K grid to cut evenly
+        GemmArgs g{};
+        g.A = Cinv; g.rsA = 1; g.csA = n; g.bsA1 = (long long)nn; g.bsA2 = (long long)(Mphi - Cinv);
+        g.B = params; g.rsB = 1; g.csB = pitch; g.bsB1 = n; g.bsB2 = 0;
+        g.C = CX; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = (long long)(MXE - CX);
+        g.M = n; g.N = n_chains; g.K = n; g.nb1 = D; g.alpha = 1.0; g.beta = 0.0;
+        g.a_band = (h->b < n - 1) ? h->b : 0;
+        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch;
+        if (g.sk_epoch == 0) g.sk_epoch = ++h->sk_epoch;
+        DCK(launch_gemm(g, 2 * D, st), "dense gemm [C~ | m~] X");
+        h->launches++;
+    }
     int rc = dense_pointwise_dispatch(h, n_chains, params, pitch, ll, grad, MXE, MXE, nullptr, nullptr, nullptr, 0, st);
     if (rc) return rc;
     DCK(gemm(Kinv, false, MXE, 1, n, (long long)plane, KE), "dense gemm K~ E");
