@@ -142,26 +142,32 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ A, 
         S[i][j] = (i >= j) ? Ad[(size_t)(j0 + j) * n + (j0 + i)] : 0.0;
     }
     __syncthreads();
+    // Right-looking factorisation with ONE block barrier per column: every thread derives the (repaired) pivot p_j itself from
+    // S[j][j] and applies the rank-1 update with the UNSCALED column, S[i][k] -= S[i][j] S[k][j] / p_j; the columns are scaled by
+    // 1 / sqrt(p_j) in one parallel pass afterwards.  (Round 1: thread 0 computed the pivot, three barriers per column.)
+    __shared__ double piv[NBMAX];
     for (int j = 0; j < nb; ++j) {
-        if (threadIdx.x == 0) {
-            double p = S[j][j];
-            if (!(p > tol)) {
-                atomicAdd(&repaired[d], 1);
-                p = (fabs(p) > tol) ? fabs(p) : (tol > 0 ? tol : 1.0);
-            }
-            S[j][j] = sqrt(p);
+        double p = S[j][j];
+        if (!(p > tol)) {
+            if (threadIdx.x == 0) atomicAdd(&repaired[d], 1);
+            p = (fabs(p) > tol) ? fabs(p) : (tol > 0 ? tol : 1.0);
         }
-        __syncthreads();
-        const double r = S[j][j];
-        for (int i = j + 1 + threadIdx.x; i < nb; i += blockDim.x) S[i][j] /= r;
-        __syncthreads();
+        if (threadIdx.x == 0) piv[j] = p;
+        const double inv_p = 1.0 / p;
         const int m = nb - j - 1;
         for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
             const int ii = j + 1 + idx % m, jj = j + 1 + idx / m;
-            if (ii >= jj) S[ii][jj] -= S[ii][j] * S[jj][j];
+            if (ii >= jj) S[ii][jj] -= S[ii][j] * S[jj][j] * inv_p;
         }
         __syncthreads();
     }
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+        const int i = idx % nb, j = idx / nb;
+        if (i > j) S[i][j] /= sqrt(piv[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < nb) S[threadIdx.x][threadIdx.x] = sqrt(piv[threadIdx.x]);
+    __syncthreads();
     // inverse of the lower-triangular block: thread c solves column c by forward substitution; X(i,c), i > c, is kept
     // at S[c][i] (the unused strict upper triangle), X(c,c) in xd[c]
     if (threadIdx.x < nb) {
