@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256) gemm_f64_dmma_kernel(const GemmArgs g) {
     __shared__ double Bs[2][GEMM_BK][GEMM_LD];
     const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
     if (g.lower_only && n0 > m0 + GEMM_BM - 1) return;
+    if (g.upper_only && m0 > n0 + GEMM_BN - 1) return;
     const int z1 = blockIdx.z % g.nb1, z2 = blockIdx.z / g.nb1;
     const double* A = g.A + z1 * g.bsA1 + z2 * g.bsA2;
     const double* B = g.B + z1 * g.bsB1 + z2 * g.bsB2;
@@ -25,6 +26,8 @@ __global__ void __launch_bounds__(256) gemm_f64_dmma_kernel(const GemmArgs g) {
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     int k_begin = 0, k_end = g.K;
     if (g.k_lo_from_tile) { int t = m0 > n0 ? m0 : n0; k_begin = (t / GEMM_BK) * GEMM_BK; }
+    if (g.b_lower && n0 > k_begin) k_begin = (n0 / GEMM_BK) * GEMM_BK;
+    if (g.a_lower && m0 + GEMM_BM < k_end) k_end = m0 + GEMM_BM;
     if (g.a_band > 0) {
         const int lo = m0 - g.a_band, hi = m0 + GEMM_BM + g.a_band;
         if (lo > k_begin) k_begin = (lo / GEMM_BK) * GEMM_BK;
@@ -216,12 +219,15 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_big_kernel(const GemmArg
     double* Bs = sm + BG_ST * BG_TILE;
     const int m0 = blockIdx.y * BG_BM, n0 = blockIdx.x * BG_BN;
     if (g.lower_only && n0 > m0 + BG_BM - 1) return;
+    if (g.upper_only && m0 > n0 + BG_BN - 1) return;
     const int z1 = blockIdx.z % g.nb1, z2 = blockIdx.z / g.nb1;
     const double* A = g.A + z1 * g.bsA1 + z2 * g.bsA2;
     const double* B = g.B + z1 * g.bsB1 + z2 * g.bsB2;
     double* C = g.C + z1 * g.bsC1 + z2 * g.bsC2;
     int k_begin = 0, k_end = g.K;
     if (g.k_lo_from_tile) { int t = m0 > n0 ? m0 : n0; k_begin = (t / BG_BK) * BG_BK; }
+    if (g.b_lower && n0 > k_begin) k_begin = (n0 / BG_BK) * BG_BK;
+    if (g.a_lower && m0 + BG_BM < k_end) k_end = m0 + BG_BM;
     if (g.a_band > 0) {
         const int lo = m0 - g.a_band, hi = m0 + BG_BM + g.a_band;
         if (lo > k_begin) k_begin = (lo / BG_BK) * BG_BK;
@@ -370,7 +376,7 @@ cudaError_t launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
         const int m_rem = g.M % BG_BM;
         const bool cut = (m_rem > 0 && m_rem <= 16 && g.M > BG_BM);
         const int tm = cut ? g.M / BG_BM : (g.M + BG_BM - 1) / BG_BM, tn = (g.N + BG_BN - 1) / BG_BN;
-        if (!no_streamk && g.sk_work && g.sk_flags && !g.lower_only && !g.k_lo_from_tile && g.a_band == 0 && sm_count <= kStreamKSlots - 1 &&
+        if (!no_streamk && g.sk_work && g.sk_flags && !g.lower_only && !g.k_lo_from_tile && !g.upper_only && !g.a_lower && !g.b_lower && g.a_band == 0 && sm_count <= kStreamKSlots - 1 &&
             (long long)tm * tn * batch >= sm_count) {
             GemmArgs m = g; if (cut) m.M = tm * BG_BM;
             cudaError_t e = ak ? (bkc ? launch_streamk<true, true>(m, tm, tn, batch, sm_count, st) : launch_streamk<true, false>(m, tm, tn, batch, sm_count, st))

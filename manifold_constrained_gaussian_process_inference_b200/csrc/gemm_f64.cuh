@@ -15,6 +15,9 @@ struct GemmArgs {
     double alpha, beta;
     int lower_only;       // skip output tiles that lie strictly above the diagonal (symmetric updates)
     int k_lo_from_tile;   // 1: A and B are lower-triangular-structured such that k < max(tile row0, tile col0) contributes 0
+    int upper_only = 0;   // skip output tiles that lie strictly below the diagonal (only the upper triangle of C is wanted)
+    int a_lower = 0;      // op(A)(m, k) is zero for k > m (lower-triangular A): k-tiles beyond the tile's last row are skipped
+    int b_lower = 0;      // op(B)(k, n) is zero for k < n (lower-triangular B): k-tiles before the tile's first column are skipped
     int a_band = 0;       // > 0: A(m, k) is zero for |m - k| > a_band (band-truncated operator): k-tiles outside the band are skipped
     // optional stream-K work space (see gemm_f64.cu): partial tiles [kStreamKSlots][128 x 128] and one flag per slot; the caller
     // owns both, zero-initialises the flags once and passes a fresh non-zero epoch per launch.  Null: data-parallel tiles only.

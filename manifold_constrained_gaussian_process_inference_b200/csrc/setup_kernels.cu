@@ -400,15 +400,19 @@ int gp_setup_device(SetupCtx& c) {
             SETUP_CUDA(launch_gemm(g, D, c.st), "mphi gemm"); c.launches++;
             SETUP_CUDA(cudaMemcpyAsync(T, Cpp, sizeof(double) * nn * D, cudaMemcpyDeviceToDevice, c.st), "copy Cpp");
             GemmArgs k = gemm_cm(mphi, false, Cp, true, T, n, n, n, n, -1.0, 1.0);               // C'' - m C'^T (:304)
+            k.upper_only = 1;                                  // Symmetric(.) reads the upper triangle only (:306)
             SETUP_CUDA(launch_gemm(k, D, c.st), "Kphi gemm"); c.launches++;
         } else {
             // stable: W = inv(L) C'^T  (X is the explicit triangular inverse; the products are Gram forms)
             GemmArgs w = gemm_cm(X, false, Cp, true, Kinv /*scratch: W*/, n, n, n, n, 1.0, 0.0);
+            w.a_lower = 1;                                     // X = inv(L) is lower triangular: half of the k-tiles are zero
             SETUP_CUDA(launch_gemm(w, D, c.st), "W gemm"); c.launches++;
             SETUP_CUDA(cudaMemcpyAsync(T, Cpp, sizeof(double) * nn * D, cudaMemcpyDeviceToDevice, c.st), "copy Cpp");
             GemmArgs k = gemm_cm(Kinv, true, Kinv, false, T, n, n, n, n, -1.0, 1.0);             // C'' - W^T W
+            k.upper_only = 1;                                  // Symmetric(.) reads the upper triangle only
             SETUP_CUDA(launch_gemm(k, D, c.st), "Kphi syrk"); c.launches++;
             GemmArgs m = gemm_cm(Kinv, true, X, false, mphi, n, n, n, n, 1.0, 0.0);              // m = W^T inv(L) = C' inv(L)^T inv(L)
+            m.b_lower = 1;                                     // inv(L)(k, j) = 0 for k < j
             SETUP_CUDA(launch_gemm(m, D, c.st), "mphi gemm"); c.launches++;
         }
         add_jitter_sym_kernel<<<eg, 256, 0, c.st>>>(T, Kphi, n, c.jitter, 1); c.launches++;       // Symmetric(K + eI) from the upper triangle (:306-307)
