@@ -1,5 +1,6 @@
 // Batched FP64 DMMA GEMM (see gemm_f64.cuh).
 #include "gemm_f64.cuh"
+#include "k1_primitives.cuh"
 #include <cstdlib>
 
 namespace magi {
@@ -98,20 +99,57 @@ __global__ void __launch_bounds__(256) gemm_f64_dmma_kernel(const GemmArgs g) {
 }
 
 // ---- large-tile kernel: 128 x 128 x 16 block tiles, 16 warps (4 x 4, warp tile 32 x 32 = 4 x 4 DMMA tiles, 16 independent
-// accumulate chains), 4-stage cp.async pipeline (8-byte copies with zero fill: the operands are arbitrary strided views, so
-// wider copies are not generally aligned), one block barrier per k-tile.  Each operand tile is staged in the direction it is
-// contiguous in global memory (template flags) with a leading dimension that makes the DMMA fragment loads conflict-free:
+// accumulate chains), 3-stage cp.async pipeline (8-byte copies with zero fill: the operands are arbitrary strided views, so
+// wider copies are not generally aligned).  The stages are handed over by mbarriers instead of a block barrier per k-tile:
+// full[s] (512 arrivals, each fired by the copy unit when a thread's copies of the tile have landed:
+// cp.async.mbarrier.arrive.noinc) and empty[s] (one arrival per warp once it has read the tile).  A tile is requested
+// BG_DIST = 1 k-tile (4096 pipe cycles) ahead into the stage that was released a whole k-tile before, so the warps of a
+// block may drift apart by a tile without anybody waiting -- with one __syncthreads per k-tile the four sub-partitions
+// drained together 80 times per output tile (ncu: 12 % barrier stalls, DMMA pipe 79.5 % busy).  Measured on the dense-mode
+// evaluation (LV n=1281, 2048 chains, ms per evaluation): block barrier, 4 stages 2.10; mbarriers with the tile requested
+// 3 / 2 / 1 tiles ahead 2.15-1.99 / 1.97 / 1.91 (requests further ahead are slower, 3 or 4 stages alike; BK = 32: 1.97).
+// Each operand tile is staged in the direction it is contiguous in global memory (template flags) with a leading dimension
+// that makes the DMMA fragment loads conflict-free:
 //   m (n)-contiguous: S[k][m], LD = 132  -> fragment word banks 8q + 2 gid      k-contiguous: S[m][k], LD = BK + 4 -> 8 gid + 2q
 // Per k4 step a warp issues 8 LDS.64 for 16 DMMAs.  Used for the dense-mode (band = n-1) operators and the large setup GEMMs.
 #ifndef MAGI_GEMM_BK
 #define MAGI_GEMM_BK 16
 #endif
 #ifndef MAGI_GEMM_ST
-#define MAGI_GEMM_ST 4
+#define MAGI_GEMM_ST 3
+#endif
+#ifndef MAGI_GEMM_MBAR
+#define MAGI_GEMM_MBAR 1
 #endif
 constexpr int BG_BM = 128, BG_BN = 128, BG_BK = MAGI_GEMM_BK, BG_ST = MAGI_GEMM_ST, BG_LDM = 132, BG_LDK = BG_BK + 4;
+#ifndef MAGI_GEMM_DIST
+#define MAGI_GEMM_DIST 1
+#endif
+constexpr int BG_DIST = MAGI_GEMM_MBAR ? MAGI_GEMM_DIST : BG_ST - 1;     // k-tiles requested ahead of the one being multiplied
 constexpr int BG_CP = BG_BM * BG_BK / 512;        // 8-byte copies per thread, operand and k-tile
 constexpr int BG_TILE = (BG_BK * BG_LDM > BG_BM * BG_LDK) ? BG_BK * BG_LDM : BG_BM * BG_LDK;   // doubles per operand stage
+constexpr size_t BG_SMEM = sizeof(double) * 2 * BG_ST * BG_TILE + sizeof(unsigned long long) * 2 * BG_ST;
+static_assert(BG_DIST >= 1 && BG_SMEM <= 227 * 1024, "pipeline depth");
+
+// stage hand-over state of a block: the barriers live behind the operand stages; j counts the k-tiles the block has
+// multiplied so far over all its output tiles / stream-K segments (tile j sits in stage j % ST, barrier phase j / ST)
+struct BigPipe {
+    unsigned long long* full;
+    unsigned long long* empty;
+    int j;
+};
+__device__ __forceinline__ BigPipe big_pipe_init(double* sm) {
+    BigPipe p;
+    p.full = reinterpret_cast<unsigned long long*>(sm + 2 * BG_ST * BG_TILE);
+    p.empty = p.full + BG_ST;
+    p.j = 0;
+    if (MAGI_GEMM_MBAR) {
+        if (threadIdx.x == 0)
+            for (int s_ = 0; s_ < BG_ST; ++s_) { mbar_init(p.full + s_, 512); mbar_init(p.empty + s_, 16); }
+        __syncthreads();
+    }
+    return p;
+}
 
 __device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -122,7 +160,7 @@ __device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* 
 // main loop over the k-tiles [kt_lo, kt_hi) of one 128 x 128 output tile (k-tile 0 starts at k_begin)
 template <bool AK, bool BKC>
 __device__ __forceinline__ void big_mainloop(const GemmArgs& g, const double* A, const double* B, int m0, int n0, int k_begin,
-                                             int kt_lo, int kt_hi, double* As, double* Bs, double (&acc)[4][4][2]) {
+                                             int kt_lo, int kt_hi, double* As, double* Bs, BigPipe& pipe, double (&acc)[4][4][2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, q = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     // this thread's BG_CP + BG_CP copies per k-tile: running global pointers, per-copy steps and row masks are set up once
@@ -145,32 +183,44 @@ __device__ __forceinline__ void big_mainloop(const GemmArgs& g, const double* A,
     int k_left_a = g.K - (k_begin + kt_lo * BG_BK + ak), k_left_b = g.K - (k_begin + kt_lo * BG_BK + bk);   // copy j is inside K iff its k offset < k_left
     auto load_tile = [&](int kt) {
         if (kt < kt_hi) {
-            const int stg = (kt - kt_lo) % BG_ST;
+            const int j = pipe.j + (kt - kt_lo), stg = j % BG_ST;
+            if (MAGI_GEMM_MBAR && j >= BG_ST) mbar_wait(pipe.empty + stg, (unsigned)((j / BG_ST) - 1) & 1u);   // tile j - ST has been read by all warps
             double* as = As + stg * BG_TILE + a_soff;
             double* bs = Bs + stg * BG_TILE + b_soff;
 #pragma unroll
-            for (int j = 0; j < BG_CP; ++j) {
-                const bool ok = ((a_mask >> j) & 1u) && (AK ? 0 : 4 * j) < k_left_a;
-                cp_async8_zfill(as + j * a_sstep, ok ? ap + j * a_step : A, ok);
-                const bool okb = ((b_mask >> j) & 1u) && (BKC ? 0 : 4 * j) < k_left_b;
-                cp_async8_zfill(bs + j * b_sstep, okb ? bp + j * b_step : B, okb);
+            for (int j_ = 0; j_ < BG_CP; ++j_) {
+                const bool ok = ((a_mask >> j_) & 1u) && (AK ? 0 : 4 * j_) < k_left_a;
+                cp_async8_zfill(as + j_ * a_sstep, ok ? ap + j_ * a_step : A, ok);
+                const bool okb = ((b_mask >> j_) & 1u) && (BKC ? 0 : 4 * j_) < k_left_b;
+                cp_async8_zfill(bs + j_ * b_sstep, okb ? bp + j_ * b_step : B, okb);
             }
             ap += a_kt; bp += b_kt; k_left_a -= BG_BK; k_left_b -= BG_BK;
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        if (MAGI_GEMM_MBAR) {
+            // fires when this thread's copies above have landed, wherever the thread is by then (no-op group when kt >= kt_hi: nobody waits for it)
+            if (kt < kt_hi) asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" :: "r"(smem_u32(pipe.full + (pipe.j + (kt - kt_lo)) % BG_ST)) : "memory");
+        } else {
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
     };
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
-    for (int s_ = 0; s_ < BG_ST - 1; ++s_) load_tile(kt_lo + s_);
+    for (int s_ = 0; s_ < BG_DIST; ++s_) load_tile(kt_lo + s_);
     for (int kt = kt_lo; kt < kt_hi; ++kt) {
-        asm volatile("cp.async.wait_group %0;\n" :: "n"(BG_ST - 2) : "memory");
-        __syncthreads();
-        load_tile(kt + BG_ST - 1);
-        const double* as = As + ((kt - kt_lo) % BG_ST) * BG_TILE;
-        const double* bs = Bs + ((kt - kt_lo) % BG_ST) * BG_TILE;
+        const int j = pipe.j + (kt - kt_lo), stg = j % BG_ST;
+        if (MAGI_GEMM_MBAR) {
+            load_tile(kt + BG_DIST);
+            mbar_wait(pipe.full + stg, (unsigned)(j / BG_ST) & 1u);                     // the copies of all 512 threads for tile kt have landed
+        } else {
+            asm volatile("cp.async.wait_group %0;\n" :: "n"(BG_ST - 2) : "memory");
+            __syncthreads();
+            load_tile(kt + BG_DIST);
+        }
+        const double* as = As + stg * BG_TILE;
+        const double* bs = Bs + stg * BG_TILE;
 #pragma unroll
         for (int k4 = 0; k4 < BG_BK / 4; ++k4) {
             double af[4], bf[4];
@@ -189,9 +239,16 @@ __device__ __forceinline__ void big_mainloop(const GemmArgs& g, const double* A,
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
+        if (MAGI_GEMM_MBAR) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pipe.empty + stg);
+        }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();          // the stages may be refilled by the next segment
+    if (!MAGI_GEMM_MBAR) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();          // the stages may be refilled by the next segment
+    }
+    pipe.j += kt_hi - kt_lo;
 }
 
 __device__ __forceinline__ void big_store(const GemmArgs& g, double* C, int m0, int n0, const double (&acc)[4][4][2]) {
@@ -235,7 +292,8 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_big_kernel(const GemmArg
     }
     const int nkt = k_end > k_begin ? (k_end - k_begin + BG_BK - 1) / BG_BK : 0;
     double acc[4][4][2];
-    big_mainloop<AK, BKC>(g, A, B, m0, n0, k_begin, 0, nkt, As, Bs, acc);
+    BigPipe pipe = big_pipe_init(sm);
+    big_mainloop<AK, BKC>(g, A, B, m0, n0, k_begin, 0, nkt, As, Bs, pipe, acc);
     big_store(g, C, m0, n0, acc);
 }
 
@@ -255,6 +313,7 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_streamk_kernel(const Gem
     long long u = units * blockIdx.x / gridDim.x;
     const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
     double acc[4][4][2];
+    BigPipe pipe = big_pipe_init(sm);
     while (u < u_end) {
         const long long tile = u / nkt;
         const int kt0 = (int)(u - tile * nkt);
@@ -265,7 +324,7 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_streamk_kernel(const Gem
         const double* B = g.B + z1 * g.bsB1 + z2 * g.bsB2;
         double* C = g.C + z1 * g.bsC1 + z2 * g.bsC2;
         const int m0 = tm * BG_BM, n0 = tn * BG_BN;
-        big_mainloop<AK, BKC>(g, A, B, m0, n0, 0, kt0, kt1, As, Bs, acc);
+        big_mainloop<AK, BKC>(g, A, B, m0, n0, 0, kt0, kt1, As, Bs, pipe, acc);
         if (kt0 > 0) {                                        // leading partial of this block: hand the accumulators to the owner
             double* w = g.sk_work + (size_t)blockIdx.x * (BG_BM * BG_BN);
 #pragma unroll
@@ -301,7 +360,7 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_dmma_streamk_kernel(const Gem
 template <bool AK, bool BKC>
 static cudaError_t launch_big(const GemmArgs& g, int batch, cudaStream_t st) {
     auto kern = gemm_f64_dmma_big_kernel<AK, BKC>;
-    const size_t smem = sizeof(double) * 2 * BG_ST * BG_TILE;
+    const size_t smem = BG_SMEM;
     static PerDeviceOnce once;       // per instantiation
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -315,7 +374,7 @@ static cudaError_t launch_big(const GemmArgs& g, int batch, cudaStream_t st) {
 template <bool AK, bool BKC>
 static cudaError_t launch_streamk(const GemmArgs& g, int tiles_m, int tiles_n, int batch, int blocks, cudaStream_t st) {
     auto kern = gemm_f64_dmma_streamk_kernel<AK, BKC>;
-    const size_t smem = sizeof(double) * 2 * BG_ST * BG_TILE;
+    const size_t smem = BG_SMEM;
     static PerDeviceOnce once;       // per instantiation
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

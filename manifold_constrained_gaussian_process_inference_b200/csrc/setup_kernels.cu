@@ -321,13 +321,13 @@ static int chol_and_inverse(SetupCtx& c, double* A, double* X, double* T, double
             g1.A = A + o21; g1.rsA = 1; g1.csA = n; g1.bsA1 = pair_stride; g1.bsA2 = (long long)n * n;
             g1.B = X + o11; g1.rsB = 1; g1.csB = n; g1.bsB1 = pair_stride; g1.bsB2 = (long long)n * n;
             g1.C = T + o21; g1.rsC = 1; g1.csC = n; g1.bsC1 = pair_stride; g1.bsC2 = (long long)n * n;
-            g1.M = m2; g1.N = (int)s; g1.K = (int)s; g1.nb1 = cnt; g1.alpha = 1.0; g1.beta = 0.0;
+            g1.M = m2; g1.N = (int)s; g1.K = (int)s; g1.nb1 = cnt; g1.alpha = 1.0; g1.beta = 0.0; g1.b_lower = 1;   // X11 is lower triangular
             SCK(launch_gemm(g1, cnt * D, c.st), "trinv gemm 1"); c.launches++;
             GemmArgs g2{};   // X21 = -X22 * T21    (m2 x s) = (m2 x m2)(m2 x s)
             g2.A = X + o22; g2.rsA = 1; g2.csA = n; g2.bsA1 = pair_stride; g2.bsA2 = (long long)n * n;
             g2.B = T + o21; g2.rsB = 1; g2.csB = n; g2.bsB1 = pair_stride; g2.bsB2 = (long long)n * n;
             g2.C = X + o21; g2.rsC = 1; g2.csC = n; g2.bsC1 = pair_stride; g2.bsC2 = (long long)n * n;
-            g2.M = m2; g2.N = (int)s; g2.K = m2; g2.nb1 = cnt; g2.alpha = -1.0; g2.beta = 0.0;
+            g2.M = m2; g2.N = (int)s; g2.K = m2; g2.nb1 = cnt; g2.alpha = -1.0; g2.beta = 0.0; g2.a_lower = 1;   // so is X22
             SCK(launch_gemm(g2, cnt * D, c.st), "trinv gemm 2"); c.launches++;
         }
     }
