@@ -91,17 +91,6 @@ __global__ void dense_e_kernel(const double* __restrict__ params, long long pitc
     }
 }
 
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    double r = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
-    return r;
-}
-
 struct DenseGradArgs {
     int n, D, K, P, n_chains, sigma_is_fixed, sigma_invalid;
     long long pitch;
@@ -117,7 +106,7 @@ struct DenseGradArgs {
 template <int MODEL>
 __global__ void __launch_bounds__(256) dense_grad_part_kernel(const DenseGradArgs a) {
     constexpr int K = DenseOde<MODEL>::K;
-    __shared__ double sh[8];
+    __shared__ double sh[8][4 + K];
     const int c = blockIdx.x, d = blockIdx.y, n = a.n, D = a.D;
     if (a.sigma_invalid) return;                                      // (the finalize kernel writes -Inf / NaN, interface.jl:192-195)
     const double* xp = a.params + (size_t)c * a.pitch;
@@ -164,15 +153,24 @@ __global__ void __launch_bounds__(256) dense_grad_part_kernel(const DenseGradArg
         bad |= gp && !isfinite(gv);            // value-only calls look at the log density alone (interface.jl:155-160)
         if (gp) gp[(size_t)d * n + i] = gv;
     }
-    eke = block_sum(eke, sh); xcx = block_sum(xcx, sh); sse = block_sum(sse, sh);
-    const double nbad = block_sum(bad ? 1.0 : 0.0, sh);
+    // one hand-over for all 4 + K sums: warp butterflies, one row of partials per warp, then thread j adds column j
+    double v[4 + K];
+    v[0] = eke; v[1] = xcx; v[2] = sse; v[3] = bad ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i < K; ++i) gth[i] = block_sum(gth[i], sh);
-    if (threadIdx.x == 0) {
-        double* r = a.part + ((size_t)c * D + d) * (4 + K);
-        r[0] = eke; r[1] = xcx; r[2] = sse; r[3] = nbad;
+    for (int i = 0; i < K; ++i) v[4 + i] = gth[i];
 #pragma unroll
-        for (int i = 0; i < K; ++i) r[4 + i] = gth[i];
+    for (int j = 0; j < 4 + K; ++j)
+        for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    const int wp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4 + K; ++j) sh[wp][j] = v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 + K) {
+        double r = 0.0;
+        for (int i = 0; i < 8; ++i) r += sh[i][threadIdx.x];
+        a.part[((size_t)c * D + d) * (4 + K) + threadIdx.x] = r;
     }
 }
 
@@ -381,7 +379,7 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         g.C = C; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = 0;
         g.M = n; g.N = n_chains; g.K = n; g.nb1 = 1 << 30; g.alpha = 1.0; g.beta = 0.0;
         g.a_band = (h->b < n - 1) ? h->b : 0;       // band-truncated operators: only the k-tiles that meet the band are multiplied
-        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch;
+        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch; g.extra_launches = &h->launches;
         if (g.sk_epoch == 0) g.sk_epoch = ++h->sk_epoch;
         cudaError_t e = launch_gemm(g, D, st);
         h->launches++;
@@ -396,7 +394,7 @@ int eval_dense_dev(magi_handle* h, int n_chains, const double* params, long long
         g.C = CX; g.rsC = 1; g.csC = n; g.bsC1 = (long long)plane; g.bsC2 = (long long)(MXE - CX);
         g.M = n; g.N = n_chains; g.K = n; g.nb1 = D; g.alpha = 1.0; g.beta = 0.0;
         g.a_band = (h->b < n - 1) ? h->b : 0;
-        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch;
+        g.sk_work = h->d_sk_work; g.sk_flags = h->d_sk_flags; g.sk_epoch = ++h->sk_epoch; g.extra_launches = &h->launches;
         if (g.sk_epoch == 0) g.sk_epoch = ++h->sk_epoch;
         DCK(launch_gemm(g, 2 * D, st), "dense gemm [C~ | m~] X");
         h->launches++;

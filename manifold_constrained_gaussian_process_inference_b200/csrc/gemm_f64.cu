@@ -384,33 +384,53 @@ static cudaError_t launch_streamk(const GemmArgs& g, int tiles_m, int tiles_n, i
     return cudaGetLastError();
 }
 
-// ---- skinny remainder: a handful of output rows (M <= 16, e.g. the 1281st row next to ten 128-row tiles).  One warp per
-// output column: lanes stride over k (B is read once, coalesced when it is k-contiguous), the few A rows come from L1/L2.
+// ---- skinny remainder: a handful of output rows (M <= 16, e.g. the 1281st row next to ten 128-row tiles).  B is read exactly
+// once: a block owns 16 output columns, two per warp, lanes stride over k (coalesced when B is k-contiguous, several loads in
+// flight per lane); the A rows, four at a time, are staged in shared memory in k-chunks, so their layout does not matter.
+constexpr int ROWS_KC = 1024, ROWS_COLS = 16;
 __global__ void __launch_bounds__(256) gemm_f64_rows_kernel(const GemmArgs g) {
+    __shared__ double As[4][ROWS_KC];
     const int z1 = blockIdx.y % g.nb1, z2 = blockIdx.y / g.nb1;
     const double* A = g.A + z1 * g.bsA1 + z2 * g.bsA2;
     const double* B = g.B + z1 * g.bsB1 + z2 * g.bsB2;
     double* C = g.C + z1 * g.bsC1 + z2 * g.bsC2;
-    const int lane = threadIdx.x & 31, c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= g.N) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = blockIdx.x * ROWS_COLS + 2 * warp;
+    const bool v0 = c0 < g.N, v1 = c0 + 1 < g.N;
     for (int r0 = 0; r0 < g.M; r0 += 4) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = lane; k < g.K; k += 32) {
-            const double b = B[(long long)k * g.rsB + (long long)c * g.csB];
+        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        for (int kc = 0; kc < g.K; kc += ROWS_KC) {
+            const int kn = g.K - kc < ROWS_KC ? g.K - kc : ROWS_KC;
+            __syncthreads();
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (r0 + i < g.M) acc[i] += A[(long long)(r0 + i) * g.rsA + (long long)k * g.csA] * b;
-        }
+                for (int k = threadIdx.x; k < kn; k += 256)
+                    As[i][k] = (r0 + i < g.M) ? A[(long long)(r0 + i) * g.rsA + (long long)(kc + k) * g.csA] : 0.0;
+            __syncthreads();
+            const double* b0 = B + (long long)c0 * g.csB + (long long)kc * g.rsB;
+            const double* b1 = b0 + g.csB;
+#pragma unroll 4
+            for (int k = lane; k < kn; k += 32) {
+                const double x0 = v0 ? b0[(long long)k * g.rsB] : 0.0, x1 = v1 ? b1[(long long)k * g.rsB] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double v = acc[i];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && r0 + i < g.M) {
-                double* p = C + (long long)(r0 + i) * g.rsC + (long long)c * g.csC;
-                v *= g.alpha;
-                *p = (g.beta == 0.0) ? v : v + g.beta * (*p);
+                for (int i = 0; i < 4; ++i) {
+                    const double av = As[i][k];
+                    acc[i][0] += av * x0;
+                    acc[i][1] += av * x1;
+                }
             }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                double v = acc[i][u];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && r0 + i < g.M && c0 + u < g.N) {
+                    double* p = C + (long long)(r0 + i) * g.rsC + (long long)(c0 + u) * g.csC;
+                    v *= g.alpha;
+                    *p = (g.beta == 0.0) ? v : v + g.beta * (*p);
+                }
+            }
     }
 }
 
@@ -443,9 +463,10 @@ cudaError_t launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
             if (e != cudaSuccess) return e;
             if (cut) {                               // bottom rows [m.M, M), all columns
                 GemmArgs r = g; r.A = g.A + (long long)m.M * g.rsA; r.C = g.C + (long long)m.M * g.rsC; r.M = g.M - m.M;
-                gemm_f64_rows_kernel<<<dim3((g.N + 7) / 8, batch), 256, 0, st>>>(r);
+                gemm_f64_rows_kernel<<<dim3((g.N + ROWS_COLS - 1) / ROWS_COLS, batch), 256, 0, st>>>(r);
                 e = cudaGetLastError();
                 if (e != cudaSuccess) return e;
+                if (g.extra_launches) ++*g.extra_launches;
             }
             return cudaSuccess;
         }

@@ -25,6 +25,7 @@ struct GemmArgs {
     unsigned* sk_flags = nullptr;
     unsigned sk_epoch = 0;
     int sm_count = 0;     // SMs of the launch device (0: queried per launch)
+    long long* extra_launches = nullptr;   // incremented when the call launches a second kernel (the skinny remainder rows)
 };
 constexpr int kStreamKSlots = 160;                       // >= SM count
 constexpr size_t kStreamKWorkDoubles = (size_t)kStreamKSlots * 128 * 128;
