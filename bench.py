@@ -198,7 +198,7 @@ def section_setup(pkg, torch, local, peaks):
                     e0.record(); tg.logdensity_and_gradient_batched_dev(nch, pt.data_ptr(), lt.data_ptr(), gt.data_ptr(), stc); e1.record()
                     torch.cuda.synchronize(); tsv.append(e0.elapsed_time(e1))
                 ms_ev = _median(tsv)
-                fl_ev = 16.0 * D * (n * 41 - 20 * 21) + n * (6 * D + 50)
+                fl_ev = float(synthetic.algorithmic_flops_per_eval(n, D, 20))      # 4 D 2 nnz + pointwise
                 tf_ev = nch * fl_ev / (ms_ev * 1e-3) * 1e-12
                 out["evaluation"] = {"config": {"workload": "lorenz96 D=%d n=%d band=20, %d chains, one GPU" % (D, n, nch)}, "ms_per_step": ms_ev,
                                      "value": nch / (ms_ev * 1e-3), "unit": "evals/s", "gpu_launches": int((tg.launch_count() - l0) // 5),

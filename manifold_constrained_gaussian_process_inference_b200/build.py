@@ -20,19 +20,25 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _deps_mtime():
-    m = 0.0
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            if f.endswith((".cuh", ".h")):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
+def _deps_mtime(path, seen=None):
+    """Newest modification time of `path` and of every header it includes (transitively, quoted includes only)."""
+    import re
+    seen = seen if seen is not None else set()
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return 0.0
+    seen.add(path)
+    m = os.path.getmtime(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', f.read(), flags=re.M):
+            m = max(m, _deps_mtime(os.path.join(os.path.dirname(path), inc), seen))
     return m
 
 
 def _compile(src, extra):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
     srcp = os.path.join(CSRC, src)
-    if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), _deps_mtime()) and not extra.get("force"):
+    if os.path.exists(obj) and os.path.getmtime(obj) >= _deps_mtime(srcp) and not extra.get("force"):
         return obj, False
     cmd = [NVCC] + FLAGS + extra.get("defs", []) + ["-c", srcp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -101,3 +101,4 @@ def test_dispatch_by_batch_size_is_seamless(pkg, monkeypatch, nc):
     tw = H.cuda_target(pkg, base)
     llw, gw = tw.logdensity_and_gradient_batched(params)
     H.assert_parity(ll, g, llw, gw, "default dispatch vs windowed, %d chains" % nc)
+

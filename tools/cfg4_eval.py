@@ -15,4 +15,9 @@ st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
     tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st)
 torch.cuda.synchronize()
-print("ok", bool(torch.isfinite(ll).all()))
+ts = []
+for _ in range(int(os.environ.get("REPS", 10))):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st); e1.record()
+    torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print("ok", bool(torch.isfinite(ll).all()), "ms per evaluation: median %.4f min %.4f" % (float(np.median(ts)), min(ts)))
