@@ -162,7 +162,7 @@ def section_dense(pkg, synthetic, torch, dev, local, peaks, reps=10):
                          "algorithmic_flops_per_eval": flops, "peak_source": peaks["fp64_src"]}}
 
 
-def section_setup(pkg, torch, local, peaks):
+def section_setup(pkg, synthetic, torch, local, peaks):
     """BASELINE config 4: Lorenz-96 D=64, n=2001: device GP setup (covariance build, blocked Cholesky, inverses, GEMMs, bands)."""
     rng = np.random.default_rng(20251018 + 3)
     n, D = 2001, 64
@@ -446,7 +446,7 @@ def main():
     if rank == 0 and "dense" in wanted:
         extra["dense"] = section_dense(pkg, synthetic, torch, dev, local, peaks)
     if rank == 0 and "setup" in wanted:
-        extra["setup"] = section_setup(pkg, torch, local, peaks)
+        extra["setup"] = section_setup(pkg, synthetic, torch, local, peaks)
         torch.cuda.empty_cache()
     if "cfg5" in wanted:
         if world > 1:
