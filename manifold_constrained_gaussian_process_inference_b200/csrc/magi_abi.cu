@@ -35,7 +35,7 @@ extern "C" int magi_destroy(magi_handle* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) free_dev(h->d_band[i]);
     for (int i = 0; i < 7; ++i) free_dev(h->d_dense[i]);
-    free_dev(h->d_fragtab); free_dev(h->d_fragtab_nat); free_dev(h->d_fragtab_bp); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
+    free_dev(h->d_fragtab); free_dev(h->d_fragtab_nat); free_dev(h->d_fragtab_bp); free_dev(h->d_steptab); free_dev(h->d_yobs); free_dev(h->d_nobs); free_dev(h->d_sigma_init);
     free_dev(h->d_params); free_dev(h->d_ll); free_dev(h->d_grad); free_dev(h->d_scratch);
     free_dev(h->d_dense_work); free_dev(h->d_dense_part); free_dev(h->d_dense_ops); free_dev(h->d_sk_work); free_dev(h->d_sk_flags);
     free_dev(h->d_small); free_dev(h->d_flow_units); if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -142,6 +142,7 @@ extern "C" int magi_create(const magi_config* cfg, magi_handle** out) {
             h->flow_fits[g] = h->flow_smem[g] <= (size_t)prop.sharedMemPerBlockOptin;
         }
         const char* force = getenv("MAGI_K1");
+        h->narrow_mode = (force && !strcmp(force, "narrow")) ? 1 : ((force && (!strcmp(force, "flow") || !strcmp(force, "windowed"))) ? -1 : 0);
         h->flow_mode = (force && !strcmp(force, "flow")) ? 1 : ((force && !strcmp(force, "windowed")) ? -1 : 0);
         if (h->flow_mode == 1 && !h->flow_fits[1]) return fail(set_error(MAGI_ERR_UNSUPPORTED, "MAGI_K1=flow: the state of 8 chains does not fit shared memory"));
         if (!h->flow_fits[1]) h->flow_mode = -1;
@@ -211,6 +212,16 @@ static int flow_groups_for(const magi_handle* h, int n_chains_call) {
     return 0;
 }
 
+// Band half-widths <= 4 of the two-component models: the FP64-FMA kernel (narrow_kernel.cuh) for batches that fill the machine
+// (one thread per chain sweeps the whole time axis: small batches are faster on the dataflow kernel).  Like the other variants
+// it is chosen by the size of the CALL (or the sampler's global chain count).
+static bool narrow_route(const magi_handle* h, int n_chains_call) {
+    if (h->narrow_mode < 0 || !narrow_supported(h->model, h->b)) return false;
+    if (h->narrow_mode > 0) return true;
+    const long long n_chains = h->dispatch_chains > 0 ? h->dispatch_chains : n_chains_call;
+    return n_chains > 16LL * h->sm_count;
+}
+
 // The two kernels read differently ordered fragment tables (the windowed kernel permutes the output slots of a tile); one
 // buffer per layout, each built on first use and whenever the band tables change.
 int refresh_fragtab(magi_handle* h, bool natural, cudaStream_t st) {
@@ -231,6 +242,7 @@ int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long p
     if (n_chains <= 0) return MAGI_OK;
     if (!h->tables_ready) return set_error(MAGI_ERR_NOT_READY, "band tables are neither built nor fully injected (magi_set_band_tables for every dim and table)");
     if (h->dense_mode) return eval_dense_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
+    if (narrow_route(h, n_chains)) return eval_narrow_dev(h, n_chains, params_dev, pitch, ll_dev, grad_dev, st);
     const int fg = flow_groups_for(h, n_chains);
     int rc = refresh_fragtab(h, fg > 0, st);
     if (rc) return rc;
@@ -427,7 +439,7 @@ extern "C" int magi_set_band_tables(magi_handle* h, int dim, int which, const do
     const int t = which - MAGI_MAT_CINV_BAND;
     CK(cudaMemcpy(h->d_band[t] + (size_t)dim * tab, in, sizeof(double) * tab, cudaMemcpyHostToDevice), "H2D band table");
     h->band_set[(size_t)t * h->D + dim] = 1;
-    h->frag_dirty = true; h->frag_nat_dirty = true; h->frag_bp_dirty = true;
+    h->frag_dirty = true; h->frag_nat_dirty = true; h->frag_bp_dirty = true; h->steptab_dirty = true;
     h->dense_band_dirty = true;
     bool all = true;
     for (char c : h->band_set) all = all && c;

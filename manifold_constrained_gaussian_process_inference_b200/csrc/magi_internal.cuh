@@ -17,6 +17,9 @@ struct magi_handle {
     double* d_fragtab_nat = nullptr;   // dataflow kernel's (natural) layout
     double* d_fragtab_bp = nullptr;    // band-product route of many-component models: natural layout, 1/beta not folded in
     bool frag_bp_dirty = true;
+    double* d_steptab = nullptr;       // K1-narrow (narrow_kernel.cuh): per-step coefficient table of band half-widths <= 4
+    bool steptab_dirty = true;
+    int narrow_mode = 0;               // 1: always when supported (MAGI_K1=narrow), -1: never, 0: by batch size
     double* d_yobs = nullptr;
     int* d_nobs = nullptr;
     double* d_sigma_init = nullptr;
@@ -69,6 +72,8 @@ int cuda_error(cudaError_t e, const char* what);
 int ensure_capacity(magi_handle* h, int n_chains);
 int refresh_fragtab(magi_handle* h, bool natural, cudaStream_t st);
 int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
+bool narrow_supported(int model, int b);
+int eval_narrow_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int eval_dense_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int run_device_setup(magi_handle* h);
 void hmc_free(magi_handle* h);

@@ -1,0 +1,382 @@
+// K1-narrow: the log posterior and its gradient (src/likelihoods.jl:43-257, src/logdensityproblems_interface.jl:176-267) for
+// band half-widths b <= 4 -- the regime where an evaluation is HBM / FP64 balanced (FN n=201, b=2 is 28 kFLOP
+// against 6.5 kB) and the DMMA tiling wastes 44-80 % of its multiplications on the parallelogram corners (a tile pair costs
+// 16 columns for 2b+1 useful ones) while its per-step fixed cost does not shrink with the band.  Plain FP64 FMAs instead:
+//
+//   * ONE THREAD PER CHAIN sweeps the time axis once.  The three operand windows (x: 4b+1 values per component, e and Ke:
+//     2b+1 each) live in registers with static indices: the sweep is a software pipeline of three stages, at step s
+//         stage 1 (t1 = s - b):   mx = m~ x,  e = f(x, theta) - mx                       (likelihoods.jl:129-130)
+//         stage 2 (t2 = s - 2b):  Ke = K~ e / beta1, sum e.Ke                            (:132, :146)
+//         stage 3 (t3 = s - 3b):  Cx = C~ x / beta2, mt = m~^T Ke, gradient, sums        (:133, :150, :179-221)
+//     TB steps are unrolled so that the windows move TB places at a time (one register move per value and TB steps);
+//   * the band coefficients of a step are the same for every chain: a per-step table [s][m~@t1 | C~@t3 | K~@t2 | m~^T@t3 | y@t3]
+//     (built once per handle, zero where a row or a column falls off the time axis, 1/beta folded in) is staged per chunk of
+//     16 steps in shared memory and read with warp-uniform (broadcast) 16-byte loads: one wavefront per two coefficients;
+//   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x 128 chains is moved with coalesced
+//     128-byte row segments and transposed through shared memory (odd row pitch: conflict-free both ways), the gradient
+//     goes back the same way, so every state byte crosses HBM exactly once in each direction.
+// Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4; per (chain, step) 8 (2b+1) + ~35
+// FP64 instructions, 4 (2b+1) + ~12 shared-memory wavefronts.
+#pragma once
+#include <cmath>
+#include "magi_internal.cuh"
+#include "ode_models.cuh"
+
+namespace magi {
+
+constexpr int kNarrowMaxChains = 256;   // chains (= threads) per block: a multiple of 32 chosen per call (whole waves of one block per SM)
+constexpr int kNarrowTCH = 16;          // steps per staged chunk
+
+struct NarrowArgs {
+    int n, P, n_chains, sigma_is_fixed, sigma_invalid, CS, n_steps_pad, n_tiles;
+    long long pitch;
+    const double* params; double* ll; double* grad;     // grad may be null (value only)
+    const double* steptab;      // [n_steps_pad][CS]: per step m~@t1 [D][W], C~@t3 [D][W], K~@t2 [D][W], m~^T@t3 [D][W], y@t3 [D] (+ pad)
+    const int* nobs; const double* sigma_init;
+    double beta3, inv_b3;
+};
+
+// per step: 4 D coefficient rows of WP = 2b + 2 doubles (2b + 1 used: even length, every row 16-byte aligned), then y[D] (+ pad)
+inline int narrow_cs(int D, int b) { const int cs = 4 * D * (2 * b + 2) + D; return (cs + 1) / 2 * 2; }
+inline int narrow_steps_pad(int n, int b) { return (n + 3 * b + kNarrowTCH - 1) / kNarrowTCH * kNarrowTCH; }
+
+// band tables are diagonal-major: T[(b + j - i) n + i] = A[i, j]
+__global__ void build_steptab_kernel(const double* __restrict__ band_cinv, const double* __restrict__ band_mphi, const double* __restrict__ band_kinv,
+                                     const double* __restrict__ yobs, double* __restrict__ steptab, int n, int b, int D, int CS, int n_steps_pad,
+                                     double scale_c, double scale_k) {
+    const int W = 2 * b + 1, WP = W + 1;
+    const size_t total = (size_t)n_steps_pad * CS, tab = (size_t)W * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(idx / CS), r = (int)(idx % CS);
+        double v = 0.0;
+        if (r < 4 * D * WP && r % WP < W) {
+            const int view = r / (D * WP), d = (r / WP) % D, o = r % WP - b;
+            const int t = s - (view == 0 ? b : (view == 2 ? 2 * b : 3 * b));     // output time of this view at step s
+            const int j = t + o;
+            if (t >= 0 && t < n && j >= 0 && j < n) {
+                if (view == 0) v = band_mphi[d * tab + (size_t)(b + o) * n + t];
+                else if (view == 1) v = band_cinv[d * tab + (size_t)(b + o) * n + t] * scale_c;
+                else if (view == 2) v = band_kinv[d * tab + (size_t)(b + o) * n + t] * scale_k;
+                else v = band_mphi[d * tab + (size_t)(b - o) * n + j];           // m~[j, t]
+            }
+        } else if (r >= 4 * D * WP && r < 4 * D * WP + D) {
+            const int d = r - 4 * D * WP, t = s - 3 * b;
+            v = (t >= 0 && t < n) ? yobs[(size_t)d * n + t] : NAN;
+        }
+        steptab[idx] = v;
+    }
+}
+
+__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gsrc, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 8 : 0;                                   // src-size 0: the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int MODEL, int B, int TB>
+__global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(const NarrowArgs a) {
+    using M = Ode<MODEL>;
+    constexpr int D = M::D, K = M::K, KX = M::KX, W = 2 * B + 1, WP = W + 1, TCH = kNarrowTCH;
+    constexpr int XW = 4 * B + TB, EW = 2 * B + TB, CS = (4 * D * WP + D + 1) / 2 * 2;        // = narrow_cs(D, B)
+    static_assert(TCH % TB == 0, "chunk / unroll");
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, NC = blockDim.x, CP = NC + 1, n = a.n;     // CP: odd row pitch of the transposed tiles
+    double* xs0 = sm;                                  // [2 buffers][D][TCH][CP] state of a chunk's times
+    double* gs = xs0 + 2 * D * TCH * CP;               // [D][TCH][CP] gradient of the chunk's stage-3 times
+    double* cf0 = gs + D * TCH * CP;                   // [2 buffers][TCH][CS] (3 D TCH CP doubles before it: even, 16-byte aligned)
+    const long long c0 = (long long)blockIdx.x * NC;
+    const long long c = c0 + tid;
+    const bool valid = c < a.n_chains;
+    const double* xp = a.params + (valid ? c : (long long)a.n_chains - 1) * a.pitch;
+    const int nxt = n * D + K;
+    const int n_chunks = a.n_steps_pad / TCH;
+    // asynchronous stage-in of chunk ch (state of times [s0, s0 + TCH) as row segments of TCH doubles, zero past the end of the
+    // axis / of the batch; the chunk's coefficient rows) into buffer ch & 1
+    // Element idx = tid + k NC of a tile: time tt = idx % TCH and dimension (idx / TCH) % D do not depend on k (NC is a multiple of
+    // TCH D = 32), the chain advances by NC / (TCH D) per k: one running pointer per thread, no index arithmetic in the loops.
+    static_assert(TCH * D <= 32 && 32 % (TCH * D) == 0, "tile mapping");
+    const int m_tt = tid % TCH, m_d = (tid / TCH) % D, m_cl = tid / (TCH * D), m_step = NC / (TCH * D), m_iter = TCH * D;
+    const int m_soff = (m_d * TCH + m_tt) * CP + m_cl;
+    auto stage_in = [&](int ch) {
+        const int s0 = ch * TCH, t = s0 + m_tt;
+        double* xs = xs0 + (ch & 1) * D * TCH * CP + m_soff;
+        const bool tok = t < n;
+        const long long rows_left = (long long)a.n_chains - c0 - m_cl;           // chains from this thread's first one to the end of the batch
+        const double* src = a.params + (c0 + m_cl) * a.pitch + (long long)m_d * n + (tok ? t : 0);
+        const long long sstep = (long long)m_step * a.pitch;
+#pragma unroll 4
+        for (int k = 0; k < m_iter; ++k) {
+            const bool ok = tok && (long long)k * m_step < rows_left;
+            cp_async8_zfill(xs + k * m_step, ok ? src : a.params, ok);
+            src += sstep;
+        }
+        const double* csrc = a.steptab + (size_t)s0 * CS;
+        double* dst = cf0 + (ch & 1) * TCH * CS;
+        for (int idx = tid; idx < TCH * CS / 2; idx += NC) cp_async16(dst + 2 * idx, csrc + 2 * idx);
+        cp_async_commit();
+    };
+    stage_in(0);
+
+    double th[KX];
+#pragma unroll
+    for (int i = 0; i < K; ++i) th[i] = xp[(size_t)n * D + i];
+    M::prepare(th);
+    double sig[D], obs_scale[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double s;
+        if (a.sigma_is_fixed) s = a.sigma_init[d];
+        else {
+            const double raw = xp[nxt + d];
+            s = isnan(raw) ? raw : exp(fmin(fmax(raw, -15.0), 15.0));     // interface.jl:200
+        }
+        sig[d] = s;
+        obs_scale[d] = (1.0 / (s * s)) * a.inv_b3;
+    }
+    double xw[D][XW], ew[D][EW], kw[D][EW];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int i = 0; i < XW; ++i) xw[d][i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < EW; ++i) { ew[d][i] = 0.0; kw[d][i] = 0.0; }
+    }
+    double eke[D], xcx[D], sse[D], gth[K];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { eke[d] = 0.0; xcx[d] = 0.0; sse[d] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < K; ++i) gth[i] = 0.0;
+    bool bad = false;
+    const bool want_grad = a.grad != nullptr;
+
+#pragma unroll 1
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int s0 = ch * TCH;
+        cp_async_wait_all();
+        __syncthreads();                     // chunk ch is in shared memory; everybody is done with chunk ch - 1 (its buffer, its gradient tile)
+        if (ch + 1 < n_chunks) stage_in(ch + 1);
+        const double* xs = xs0 + (ch & 1) * D * TCH * CP;
+        const double* cf = cf0 + (ch & 1) * TCH * CS;
+#pragma unroll 1
+        for (int sb = 0; sb < TCH / TB; ++sb) {
+            // Stage-major over the TB unrolled steps: the TB band products of a stage are independent dependency chains (a
+            // step-major body is one long chain per step, and its shared-memory stores keep the next step's loads behind them).
+            const double* cfb = cf + sb * TB * CS;
+            // coefficient o of row (view v, dimension d) of step u: rows are 16-byte aligned, one LDS.128 per two coefficients
+            auto coef = [&](const double2* row, int o) { const double2 p = row[o >> 1]; return (o & 1) ? p.y : p.x; };
+#pragma unroll
+            for (int u = 0; u < TB; ++u)
+#pragma unroll
+                for (int d = 0; d < D; ++d) xw[d][4 * B + u] = xs[(d * TCH + sb * TB + u) * CP + tid];
+            // ---- stage 1: t1 = s - B ----
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const double* cfs = cfb + u * CS;
+                const int t1 = s0 + sb * TB + u - B;
+                double xa[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xa[d] = xw[d][3 * B + u];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double2* r0 = reinterpret_cast<const double2*>(cfs + (0 * D + d) * WP);
+                    double mx0 = 0.0, mx1 = 0.0;                 // two partial sums: half the dependent-FMA chain
+#pragma unroll
+                    for (int o = 0; o < W; ++o) {
+                        if (o & 1) mx1 += coef(r0, o) * xw[d][2 * B + u + o];                       // likelihoods.jl:129
+                        else mx0 += coef(r0, o) * xw[d][2 * B + u + o];
+                    }
+                    const double e = M::f(d, xa, th) - (mx0 + mx1);                                              // :130
+                    ew[d][2 * B + u] = (t1 >= 0 && t1 < n) ? e : 0.0;
+                }
+            }
+            // ---- stage 2: t2 = s - 2B ----
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const double* cfs = cfb + u * CS;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double2* r2 = reinterpret_cast<const double2*>(cfs + (2 * D + d) * WP);
+                    double ke0 = 0.0, ke1 = 0.0;
+#pragma unroll
+                    for (int o = 0; o < W; ++o) {
+                        if (o & 1) ke1 += coef(r2, o) * ew[d][u + o];                               // :132 (1/beta1 in the table)
+                        else ke0 += coef(r2, o) * ew[d][u + o];
+                    }
+                    const double ke = ke0 + ke1;
+                    kw[d][2 * B + u] = ke;
+                    eke[d] += ew[d][B + u] * ke;                                                                 // :146
+                }
+            }
+            // ---- stage 3: t3 = s - 3B (outside the time axis x, Ke, the coefficients and hence every term are zero) ----
+            double gvo[TB][D];
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const double* cfs = cfb + u * CS;
+                const int t3 = s0 + sb * TB + u - 3 * B;
+                double xa[D], wa[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) { xa[d] = xw[d][B + u]; wa[d] = kw[d][B + u]; }
+                const bool live = t3 >= 0 && t3 < n;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double2* r1 = reinterpret_cast<const double2*>(cfs + (1 * D + d) * WP);
+                    const double2* r3 = reinterpret_cast<const double2*>(cfs + (3 * D + d) * WP);
+                    double cx0 = 0.0, cx1 = 0.0, mt0 = 0.0, mt1 = 0.0;
+#pragma unroll
+                    for (int o = 0; o < W; ++o) {
+                        if (o & 1) { cx1 += coef(r1, o) * xw[d][u + o]; mt1 += coef(r3, o) * kw[d][u + o]; }
+                        else { cx0 += coef(r1, o) * xw[d][u + o]; mt0 += coef(r3, o) * kw[d][u + o]; }   // :133 (1/beta2 in the table), :192
+                    }
+                    const double cx = cx0 + cx1, mt = mt0 + mt1;
+                    const double y = cfs[4 * D * WP + d];
+                    const bool fin = live && isfinite(y);                                                        // :123
+                    const double e0 = fin ? xa[d] - y : 0.0;
+                    double gv = -(e0 * obs_scale[d]);                                                            // :179
+                    gv -= cx;                                                                                    // :186
+                    gv += mt;                                                                                    // :194
+                    M::jx_col_sub(d, xa, th, wa, gv);                                                            // :214-216
+                    M::jth_row_sub(d, xa, th, wa[d], gth);                                                       // :219-221
+                    bad |= want_grad && !isfinite(gv);
+                    xcx[d] += xa[d] * cx;                                                                        // :150
+                    sse[d] += e0 * e0;                                                                           // :139
+                    gvo[u][d] = gv;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TB; ++u)
+#pragma unroll
+                for (int d = 0; d < D; ++d) gs[(d * TCH + sb * TB + u) * CP + tid] = gvo[u][d];
+            // the windows move TB places
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+#pragma unroll
+                for (int i = 0; i < XW - TB; ++i) xw[d][i] = xw[d][i + TB];
+#pragma unroll
+                for (int i = 0; i < EW - TB; ++i) { ew[d][i] = ew[d][i + TB]; kw[d][i] = kw[d][i + TB]; }
+            }
+        }
+        __syncthreads();
+        // ---- stage out: gradient of times [s0 - 3B, s0 + TCH - 3B) ----
+        if (want_grad) {
+            const int t = s0 + m_tt - 3 * B;
+            if (t >= 0 && t < n) {
+                const long long rows_left = (long long)a.n_chains - c0 - m_cl;
+                double* dst = a.grad + (c0 + m_cl) * a.pitch + (long long)m_d * n + t;
+                const long long sstep = (long long)m_step * a.pitch;
+                const double* g = gs + m_soff;
+#pragma unroll 4
+                for (int k = 0; k < m_iter; ++k) {
+                    if ((long long)k * m_step < rows_left) *dst = g[k * m_step];
+                    dst += sstep;
+                }
+            }
+        }
+    }
+    __syncthreads();       // every x-gradient store of the block is issued before a guard below overwrites a chain's row
+
+    // ---------------- per chain: log density in the reference's order of accumulation, sigma gradient, guards ----------------
+    if (!valid) return;
+    double* gp = want_grad ? a.grad + c * a.pitch : nullptr;
+    const int P = a.P;
+    if (a.sigma_invalid) {                                            // interface.jl:192-195
+        a.ll[c] = -INFINITY;
+        if (gp) for (int i = 0; i < P; ++i) gp[i] = NAN;
+        return;
+    }
+    double ll = 0.0, prior = 0.0, gsig[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double s = sig[d], s2 = s * s;
+        const int nobs = a.nobs[d];
+        double ll_obs = -0.5 * sse[d] / s2;                           // likelihoods.jl:139
+        if (nobs > 0) ll_obs -= 0.5 * nobs * log(2.0 * M_PI * s2);   // :141
+        ll += ll_obs / a.beta3;                                       // :143
+        ll += -0.5 * eke[d];                                          // :146-147 (1/beta1 folded into K~)
+        ll += -0.5 * xcx[d];                                          // :150-151 (1/beta2 folded into C~)
+        gsig[d] = (s > 0 && nobs > 0) ? (sse[d] / s2 - nobs) / (s * a.beta3) : 0.0;   // :229-246
+        if (gp) bad |= !isfinite(gsig[d]);
+        if (!a.sigma_is_fixed) {
+            const double raw = xp[nxt + d];
+            prior += isnan(raw) ? raw : fmin(fmax(raw, -15.0), 15.0);  // interface.jl:206
+        }
+    }
+    if (gp) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) bad |= !isfinite(gth[i]);
+    }
+    bad |= !isfinite(ll);
+    if (bad) {                                                        // interface.jl:222-226
+        a.ll[c] = -INFINITY;
+        if (gp) for (int i = 0; i < P; ++i) gp[i] = 0.0;
+        return;
+    }
+    double total = ll;
+    bool bad2 = false;
+    double gls[D];
+    if (!a.sigma_is_fixed) {
+        total += prior;                                               // interface.jl:238
+#pragma unroll
+        for (int d = 0; d < D; ++d) { gls[d] = gsig[d] * sig[d] + 1.0; bad2 |= !isfinite(gls[d]); }   // :249-253
+    }
+    a.ll[c] = total;
+    if (gp) {
+        if (bad2) { for (int i = 0; i < P; ++i) gp[i] = 0.0; }       // interface.jl:260-264
+        else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) gp[n * D + i] = gth[i];
+            if (!a.sigma_is_fixed) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) gp[nxt + d] = gls[d];
+            }
+        }
+    }
+}
+
+// Chains per block: one block per SM (its tiles take most of the shared memory), so the batch should come in whole waves of
+// sm_count blocks -- the multiple of 32 that needs the fewest waves, the larger one on a tie (more warps per SM).
+inline int narrow_block_chains(int n_chains, int sm_count) {
+    int best = 32; long long best_cost = -1;
+    for (int nc = 32; nc <= kNarrowMaxChains; nc += 32) {
+        const long long tiles = (n_chains + nc - 1) / nc, waves = (tiles + sm_count - 1) / sm_count;
+        const long long cost = waves * (100 + nc);          // a wave of wider blocks takes longer, but far less than proportionally
+        if (best_cost < 0 || cost <= best_cost) { best = nc; best_cost = cost; }
+    }
+    return best;
+}
+
+template <int MODEL, int B>
+static cudaError_t narrow_launch_b(const NarrowArgs& a, int sm_count, cudaStream_t st) {
+    constexpr int TB = (B <= 2) ? 4 : 2;
+    constexpr int D = Ode<MODEL>::D;
+    auto kern = narrow_logpost_kernel<MODEL, B, TB>;
+    const int nc = narrow_block_chains(a.n_chains, sm_count), CP = nc + 1;
+    const size_t smem = sizeof(double) * ((size_t)3 * D * kNarrowTCH * CP + 1 + (size_t)2 * kNarrowTCH * a.CS);
+    static PerDeviceOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const int blocks = (a.n_chains + nc - 1) / nc;
+    kern<<<blocks, nc, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t narrow_launch_model(const NarrowArgs& a, int b, int sm_count, cudaStream_t st) {
+    switch (b) {
+    case 0: return narrow_launch_b<MODEL, 0>(a, sm_count, st);
+    case 1: return narrow_launch_b<MODEL, 1>(a, sm_count, st);
+    case 2: return narrow_launch_b<MODEL, 2>(a, sm_count, st);
+    case 3: return narrow_launch_b<MODEL, 3>(a, sm_count, st);
+    case 4: return narrow_launch_b<MODEL, 4>(a, sm_count, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace magi

@@ -482,7 +482,7 @@ int run_device_setup(magi_handle* h) {
     h->setup_alloc_ms = alloc_dense_ms + c.alloc_ms; h->setup_kernel_ms = c.kernel_ms;
     h->repaired_c = c.rep_c; h->repaired_k = c.rep_k;
     std::fill(h->band_set.begin(), h->band_set.end(), 1);
-    h->tables_ready = true; h->frag_dirty = true; h->frag_nat_dirty = true; h->frag_bp_dirty = true; h->dense_band_dirty = true;
+    h->tables_ready = true; h->frag_dirty = true; h->frag_nat_dirty = true; h->frag_bp_dirty = true; h->steptab_dirty = true; h->dense_band_dirty = true;
     return MAGI_OK;
 }
 

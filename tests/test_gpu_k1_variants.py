@@ -102,3 +102,52 @@ def test_dispatch_by_batch_size_is_seamless(pkg, monkeypatch, nc):
     llw, gw = tw.logdensity_and_gradient_batched(params)
     H.assert_parity(ll, g, llw, gw, "default dispatch vs windowed, %d chains" % nc)
 
+
+
+@pytest.mark.parametrize("model,n,b,nc,kw", [
+    ("fn", 201, 4, 300, {"T": 20.0, "obs_every": 5}),        # three blocks of 128 chains, the last one partial
+    ("fn", 201, 2, 140, {"beta": (2.0, 3.0, 5.0)}),
+    ("fn", 201, 3, 129, {}),
+    ("fn", 41, 1, 37, {}),
+    ("fn", 16, 0, 8, {}),                                    # diagonal band
+    ("fn", 9, 1, 3, {}),
+    ("fn", 7, 4, 5, {}),                                     # band wider than half the time axis
+    ("fn", 1, 0, 2, {"obs_every": 1}),
+    ("fn", 50, 4, 12, {"sigma_fixed": True}),
+    ("lv", 81, 3, 130, {"T": 4.0}),
+    ("lv", 33, 2, 17, {"T": 4.0, "beta": (1.0, 1.0, 5.0)}),
+])
+def test_narrow_kernel_matches_the_oracle(pkg, monkeypatch, model, n, b, nc, kw):
+    """K1-narrow (narrow_kernel.cuh: FP64-FMA sweep, one thread per chain, band half-widths <= 4) against the oracle and against
+    the windowed DMMA kernel on identical inputs."""
+    prob = H.make_problem(model=model, n=n, b=b, n_chains=nc, seed=11 * n + b, **kw)
+    ll_ref, g_ref = H.oracle_batched(prob)
+    tg = _target(pkg, prob, monkeypatch, "narrow")
+    ll, g = tg.logdensity_and_gradient_batched(prob["params"])
+    H.assert_parity(ll, g, ll_ref, g_ref, "narrow %s n=%d b=%d" % (model, n, b))
+    ll2, _ = tg.logdensity_and_gradient_batched(prob["params"], want_grad=False)
+    assert np.array_equal(ll, ll2)
+    ll3, g3 = tg.logdensity_and_gradient_batched(prob["params"][::-1].copy())      # a chain gives the same bits wherever it sits
+    assert np.array_equal(ll, ll3[::-1]) and np.array_equal(g, g3[::-1])
+    tg.close()
+    tw = _target(pkg, prob, monkeypatch, "windowed")
+    llw, gw = tw.logdensity_and_gradient_batched(prob["params"])
+    H.assert_parity(ll, g, llw, gw, "narrow vs windowed")
+
+
+def test_narrow_kernel_guards_are_per_chain(pkg, monkeypatch):
+    """interface.jl:222-226, 260-264 per chain on K1-narrow."""
+    prob = H.make_problem(model="fn", n=41, b=3, n_chains=20, seed=5)
+    tg = _target(pkg, prob, monkeypatch, "narrow")
+    ll0, g0 = tg.logdensity_and_gradient_batched(prob["params"])
+    bad = prob["params"].copy()
+    bad[3, 7] = np.nan
+    bad[9, 2 * 41 + 2] = np.inf
+    bad[17, 2 * 41 + 3] = np.nan
+    ll, g = tg.logdensity_and_gradient_batched(bad)
+    for c in (3, 9, 17):
+        assert ll[c] == -np.inf and np.all(g[c] == 0.0)
+    keep = np.setdiff1d(np.arange(20), [3, 9, 17])
+    assert np.array_equal(ll[keep], ll0[keep]) and np.array_equal(g[keep], g0[keep])
+    ll_ref, g_ref = H.oracle_batched(prob, bad)
+    H.assert_parity(ll, g, ll_ref, g_ref, "guards")
