@@ -162,6 +162,43 @@ def section_dense(pkg, synthetic, torch, dev, local, peaks, reps=10):
                          "algorithmic_flops_per_eval": flops, "peak_source": peaks["fp64_src"]}}
 
 
+def section_smallband(pkg, synthetic, torch, dev, local, peaks, reps=10):
+    """The north-star HBM regime: FN n=201 with band half-widths 1, 2 and 4, 65 536 chains on one GPU (427 MB of state + gradient per
+    pass: nothing fits the 126 MB L2).  Large batches of these bands run on K1-narrow (csrc/narrow_kernel.cuh)."""
+    nch = 65536
+    out = {"config": {"workload": "fn201 small bands: fn n=201 D=2 k=3 band in (1, 2, 4) matern52 jitter=1e-6, %d chains, one GPU" % nch},
+           "l2": "427 MB of parameters + gradient per pass > 126 MB L2, no explicit flush", "bands": {}}
+    w = synthetic.make_workload("fn201", nch)
+    n, D = w["n"], w["D"]
+    p = torch.from_numpy(w["params"]).to(dev); g = torch.empty_like(p); ll = torch.empty(nch, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    P = p.shape[1]
+    sampler = ClockSampler(local); sampler.start()
+    for b in (1, 2, 4):
+        tg = pkg.MagiTarget.from_config(w["yobs"], w["tvec"], w["phi"], pkg.fn_system(), w["sigma_init"], bandsize=b, jitter=1e-6,
+                                        setup_mode="stable", device=local, max_chains=8)
+        for _ in range(3):
+            tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st)
+        torch.cuda.synchronize()
+        l0 = tg.launch_count(); ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); tg.logdensity_and_gradient_batched_dev(nch, p.data_ptr(), ll.data_ptr(), g.data_ptr(), st); e1.record()
+            torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        ms = _median(ts)
+        flops, abytes = synthetic.algorithmic_flops_per_eval(n, D, b), synthetic.algorithmic_bytes_per_eval(P)
+        gbs, tf = nch * abytes / (ms * 1e-3) * 1e-9, nch * flops / (ms * 1e-3) * 1e-12
+        out["bands"][str(b)] = {"ms_per_step": ms, "ms_min": min(ts), "ms_max": max(ts), "value": nch / (ms * 1e-3), "unit": "evals/s",
+                                "gpu_launches": int((tg.launch_count() - l0) // reps), "ll_finite": bool(torch.isfinite(ll).all().item()),
+                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                             "kernel": "narrow_logpost_kernel", "algorithmic_bytes_per_eval": abytes, "peak_source": peaks["hbm_src"]},
+                                "roofline_fp64": {"bound": "fp64", "achieved": tf, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["fp64_tflops"],
+                                                  "algorithmic_flops_per_eval": flops}}
+        tg.close()
+    out["clocks"] = sampler.stop()
+    return out
+
+
 def section_setup(pkg, synthetic, torch, local, peaks):
     """BASELINE config 4: Lorenz-96 D=64, n=2001: device GP setup (covariance build, blocked Cholesky, inverses, GEMMs, bands)."""
     rng = np.random.default_rng(20251018 + 3)
@@ -303,7 +340,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--repeats", type=int, default=20, help="repetitions of the timed block of --steps launches")
-    ap.add_argument("--sections", default="dense,setup,cfg5", help="extra measurements of the own arm (comma list or 'none')")
+    ap.add_argument("--sections", default="dense,setup,smallband,cfg5", help="extra measurements of the own arm (comma list or 'none')")
     ap.add_argument("--cfg5-chains", type=int, default=65536)
     ap.add_argument("--cfg5-iters", type=int, default=240, help="HMC iterations of the cfg5 section (half of them warm-up)")
     args = ap.parse_args()
@@ -447,6 +484,9 @@ def main():
         extra["dense"] = section_dense(pkg, synthetic, torch, dev, local, peaks)
     if rank == 0 and "setup" in wanted:
         extra["setup"] = section_setup(pkg, synthetic, torch, local, peaks)
+        torch.cuda.empty_cache()
+    if rank == 0 and "smallband" in wanted:
+        extra["smallband"] = section_smallband(pkg, synthetic, torch, dev, local, peaks)
         torch.cuda.empty_cache()
     if "cfg5" in wanted:
         if world > 1:

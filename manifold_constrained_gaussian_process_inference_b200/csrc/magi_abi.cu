@@ -213,13 +213,14 @@ static int flow_groups_for(const magi_handle* h, int n_chains_call) {
 }
 
 // Band half-widths <= 4 of the two-component models: the FP64-FMA kernel (narrow_kernel.cuh) for batches that fill the machine
-// (one thread per chain sweeps the whole time axis: small batches are faster on the dataflow kernel).  Like the other variants
-// it is chosen by the size of the CALL (or the sampler's global chain count).
+// (one thread per chain sweeps the whole time axis: below ~8192 chains the DMMA kernels are faster -- FN n=201, b=2: 4096 chains
+// 0.049 against 0.036 ms, 16 384 chains 0.074 against 0.104 ms).  Like the other variants it is chosen by the size of the CALL (or
+// the sampler's global chain count), so how a batch is cut never changes the bits.
 static bool narrow_route(const magi_handle* h, int n_chains_call) {
     if (h->narrow_mode < 0 || !narrow_supported(h->model, h->b)) return false;
     if (h->narrow_mode > 0) return true;
     const long long n_chains = h->dispatch_chains > 0 ? h->dispatch_chains : n_chains_call;
-    return n_chains > 16LL * h->sm_count;
+    return n_chains >= (h->b <= 2 ? 8192 : 32768);
 }
 
 // The two kernels read differently ordered fragment tables (the windowed kernel permutes the output slots of a tile); one
@@ -359,7 +360,7 @@ extern "C" int magi_logdensity_and_gradient_batched(magi_handle* h, int n_chains
     if (n_chains >= 2 * chunk_min && !h->dense_mode && (h->scratch_in_smem || chunk_flow) && h->tables_ready) {
         for (int i = 0; i < 3; ++i)
             if (!h->pipe_streams[i]) CK(cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
-        rc = refresh_fragtab(h, chunk_flow, h->stream);
+        rc = narrow_route(h, n_chains) ? refresh_steptab(h, h->stream) : refresh_fragtab(h, chunk_flow, h->stream);      // built before the chunks' streams use it
         if (rc) return rc;
         CK(cudaStreamSynchronize(h->stream), "stream sync");
         int i = 0;

@@ -73,6 +73,7 @@ int ensure_capacity(magi_handle* h, int n_chains);
 int refresh_fragtab(magi_handle* h, bool natural, cudaStream_t st);
 int eval_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 bool narrow_supported(int model, int b);
+int refresh_steptab(magi_handle* h, cudaStream_t st);
 int eval_narrow_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int eval_dense_dev(magi_handle* h, int n_chains, const double* params_dev, long long pitch, double* ll_dev, double* grad_dev, cudaStream_t st);
 int run_device_setup(magi_handle* h);

@@ -15,8 +15,11 @@
 //   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x 128 chains is moved with coalesced
 //     128-byte row segments and transposed through shared memory (odd row pitch: conflict-free both ways), the gradient
 //     goes back the same way, so every state byte crosses HBM exactly once in each direction.
-// Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4; per (chain, step) 8 (2b+1) + ~35
-// FP64 instructions, 4 (2b+1) + ~12 shared-memory wavefronts.
+// Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4.  What binds it in practice is the
+// coefficient broadcast: a warp-uniform 8- or 16-byte shared-memory load costs 2 / 4 wavefronts whatever the address pattern, i.e.
+// 2 wavefronts per coefficient and 32 chains: 8 D (2b+1) per step, 144 at b = 4 -- the tensor core of the DMMA kernels is, among
+// other things, the broadcast engine this kernel lacks.  Measured (FN n=201, 65 536 chains, one B200): b = 1 / 2 / 4 0.180 / 0.203 /
+// 0.306 ms against 0.414 ms for the windowed DMMA kernel (2350 / 2100 / 1395 GB/s algorithmic: 0.36 / 0.32 / 0.22 of the HBM peak).
 #pragma once
 #include <cmath>
 #include "magi_internal.cuh"
@@ -25,19 +28,19 @@
 namespace magi {
 
 constexpr int kNarrowMaxChains = 256;   // chains (= threads) per block: a multiple of 32 chosen per call (whole waves of one block per SM)
-constexpr int kNarrowTCH = 16;          // steps per staged chunk
+constexpr int kNarrowTCH = 16;          // steps the per-step table is padded to (the largest staged chunk)
 
 struct NarrowArgs {
     int n, P, n_chains, sigma_is_fixed, sigma_invalid, CS, n_steps_pad, n_tiles;
     long long pitch;
     const double* params; double* ll; double* grad;     // grad may be null (value only)
-    const double* steptab;      // [n_steps_pad][CS]: per step m~@t1 [D][W], C~@t3 [D][W], K~@t2 [D][W], m~^T@t3 [D][W], y@t3 [D] (+ pad)
+    const double* steptab;      // [n_steps_pad][CS]: per step m~@t1 [D][W], C~@t3 [D][W], K~@t2 [D][W], m~^T@t3 [D][WP], (y, weight)@t3 [D][2]
     const int* nobs; const double* sigma_init;
     double beta3, inv_b3;
 };
 
-// per step: 4 D coefficient rows of WP = 2b + 2 doubles (2b + 1 used: even length, every row 16-byte aligned), then y[D] (+ pad)
-inline int narrow_cs(int D, int b) { const int cs = 4 * D * (2 * b + 2) + D; return (cs + 1) / 2 * 2; }
+// per step: 4 D coefficient rows of WP = 2b + 2 doubles (2b + 1 used: even length, every row 16-byte aligned), then (y, weight)[D]
+inline int narrow_cs(int D, int b) { return 4 * D * (2 * b + 2) + 2 * D; }
 inline int narrow_steps_pad(int n, int b) { return (n + 3 * b + kNarrowTCH - 1) / kNarrowTCH * kNarrowTCH; }
 
 // band tables are diagonal-major: T[(b + j - i) n + i] = A[i, j]
@@ -59,9 +62,10 @@ __global__ void build_steptab_kernel(const double* __restrict__ band_cinv, const
                 else if (view == 2) v = band_kinv[d * tab + (size_t)(b + o) * n + t] * scale_k;
                 else v = band_mphi[d * tab + (size_t)(b - o) * n + j];           // m~[j, t]
             }
-        } else if (r >= 4 * D * WP && r < 4 * D * WP + D) {
-            const int d = r - 4 * D * WP, t = s - 3 * b;
-            v = (t >= 0 && t < n) ? yobs[(size_t)d * n + t] : NAN;
+        } else if (r >= 4 * D * WP) {                         // (y, 1) where dimension d is observed at t3, (0, 0) elsewhere
+            const int d = (r - 4 * D * WP) >> 1, t = s - 3 * b;
+            const double y = (t >= 0 && t < n) ? yobs[(size_t)d * n + t] : NAN;
+            v = isfinite(y) ? (((r - 4 * D * WP) & 1) ? 1.0 : y) : 0.0;
         }
         steptab[idx] = v;
     }
@@ -79,11 +83,12 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int MODEL, int B, int TB>
-__global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(const NarrowArgs a) {
+// TCH: steps per staged chunk; BPS: blocks per SM (1: up to 256 chains per block and 255 registers; 4: 128 chains and 128 registers)
+template <int MODEL, int B, int TB, int TCH, int BPS>
+__global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow_logpost_kernel(const NarrowArgs a) {
     using M = Ode<MODEL>;
-    constexpr int D = M::D, K = M::K, KX = M::KX, W = 2 * B + 1, WP = W + 1, TCH = kNarrowTCH;
-    constexpr int XW = 4 * B + TB, EW = 2 * B + TB, CS = (4 * D * WP + D + 1) / 2 * 2;        // = narrow_cs(D, B)
+    constexpr int D = M::D, K = M::K, KX = M::KX, W = 2 * B + 1, WP = W + 1;
+    constexpr int XW = 4 * B + TB, EW = 2 * B + TB, CS = 4 * D * WP + 2 * D;        // = narrow_cs(D, B)
     static_assert(TCH % TB == 0, "chunk / unroll");
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, NC = blockDim.x, CP = NC + 1, n = a.n;     // CP: odd row pitch of the transposed tiles
@@ -185,13 +190,10 @@ __global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(con
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     const double2* r0 = reinterpret_cast<const double2*>(cfs + (0 * D + d) * WP);
-                    double mx0 = 0.0, mx1 = 0.0;                 // two partial sums: half the dependent-FMA chain
+                    double mx = coef(r0, 0) * xw[d][2 * B + u];     // (TB x D independent chains per stage: no partial sums needed)
 #pragma unroll
-                    for (int o = 0; o < W; ++o) {
-                        if (o & 1) mx1 += coef(r0, o) * xw[d][2 * B + u + o];                       // likelihoods.jl:129
-                        else mx0 += coef(r0, o) * xw[d][2 * B + u + o];
-                    }
-                    const double e = M::f(d, xa, th) - (mx0 + mx1);                                              // :130
+                    for (int o = 1; o < W; ++o) mx += coef(r0, o) * xw[d][2 * B + u + o];                        // likelihoods.jl:129
+                    const double e = M::f(d, xa, th) - mx;                                                       // :130
                     ew[d][2 * B + u] = (t1 >= 0 && t1 < n) ? e : 0.0;
                 }
             }
@@ -202,13 +204,9 @@ __global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(con
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     const double2* r2 = reinterpret_cast<const double2*>(cfs + (2 * D + d) * WP);
-                    double ke0 = 0.0, ke1 = 0.0;
+                    double ke = coef(r2, 0) * ew[d][u];
 #pragma unroll
-                    for (int o = 0; o < W; ++o) {
-                        if (o & 1) ke1 += coef(r2, o) * ew[d][u + o];                               // :132 (1/beta1 in the table)
-                        else ke0 += coef(r2, o) * ew[d][u + o];
-                    }
-                    const double ke = ke0 + ke1;
+                    for (int o = 1; o < W; ++o) ke += coef(r2, o) * ew[d][u + o];                                // :132 (1/beta1 in the table)
                     kw[d][2 * B + u] = ke;
                     eke[d] += ew[d][B + u] * ke;                                                                 // :146
                 }
@@ -218,25 +216,18 @@ __global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(con
 #pragma unroll
             for (int u = 0; u < TB; ++u) {
                 const double* cfs = cfb + u * CS;
-                const int t3 = s0 + sb * TB + u - 3 * B;
                 double xa[D], wa[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) { xa[d] = xw[d][B + u]; wa[d] = kw[d][B + u]; }
-                const bool live = t3 >= 0 && t3 < n;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     const double2* r1 = reinterpret_cast<const double2*>(cfs + (1 * D + d) * WP);
                     const double2* r3 = reinterpret_cast<const double2*>(cfs + (3 * D + d) * WP);
-                    double cx0 = 0.0, cx1 = 0.0, mt0 = 0.0, mt1 = 0.0;
+                    double cx = coef(r1, 0) * xw[d][u], mt = coef(r3, 0) * kw[d][u];
 #pragma unroll
-                    for (int o = 0; o < W; ++o) {
-                        if (o & 1) { cx1 += coef(r1, o) * xw[d][u + o]; mt1 += coef(r3, o) * kw[d][u + o]; }
-                        else { cx0 += coef(r1, o) * xw[d][u + o]; mt0 += coef(r3, o) * kw[d][u + o]; }   // :133 (1/beta2 in the table), :192
-                    }
-                    const double cx = cx0 + cx1, mt = mt0 + mt1;
-                    const double y = cfs[4 * D * WP + d];
-                    const bool fin = live && isfinite(y);                                                        // :123
-                    const double e0 = fin ? xa[d] - y : 0.0;
+                    for (int o = 1; o < W; ++o) { cx += coef(r1, o) * xw[d][u + o]; mt += coef(r3, o) * kw[d][u + o]; }   // :133 (1/beta2 in the table), :192
+                    const double2 yw = reinterpret_cast<const double2*>(cfs + 4 * D * WP)[d];    // (y, 1) for an observation, (0, 0) otherwise
+                    const double e0 = (xa[d] - yw.x) * yw.y;                                                     // :123 (missing: e0 = 0)
                     double gv = -(e0 * obs_scale[d]);                                                            // :179
                     gv -= cx;                                                                                    // :186
                     gv += mt;                                                                                    // :194
@@ -340,10 +331,10 @@ __global__ void __launch_bounds__(kNarrowMaxChains, 1) narrow_logpost_kernel(con
 
 // Chains per block: one block per SM (its tiles take most of the shared memory), so the batch should come in whole waves of
 // sm_count blocks -- the multiple of 32 that needs the fewest waves, the larger one on a tie (more warps per SM).
-inline int narrow_block_chains(int n_chains, int sm_count) {
+inline int narrow_block_chains(int n_chains, int sm_count, int max_chains, int bps) {
     int best = 32; long long best_cost = -1;
-    for (int nc = 32; nc <= kNarrowMaxChains; nc += 32) {
-        const long long tiles = (n_chains + nc - 1) / nc, waves = (tiles + sm_count - 1) / sm_count;
+    for (int nc = 32; nc <= max_chains; nc += 32) {
+        const long long tiles = (n_chains + nc - 1) / nc, waves = (tiles + (long long)sm_count * bps - 1) / ((long long)sm_count * bps);
         const long long cost = waves * (100 + nc);          // a wave of wider blocks takes longer, but far less than proportionally
         if (best_cost < 0 || cost <= best_cost) { best = nc; best_cost = cost; }
     }
@@ -353,13 +344,16 @@ inline int narrow_block_chains(int n_chains, int sm_count) {
 template <int MODEL, int B>
 static cudaError_t narrow_launch_b(const NarrowArgs& a, int sm_count, cudaStream_t st) {
     constexpr int TB = (B <= 2) ? 4 : 2;
+    // one 8-warp block per SM at up to 255 registers; four 4-warp blocks at 128 registers and 8-step chunks (BPS = 4) were measured
+    // slower (b = 1, 65 536 chains: 0.250 against 0.180 ms): the kernel is bound by shared-memory wavefronts, not by latency
+    constexpr int BPS = 1, TCH = 16;
     constexpr int D = Ode<MODEL>::D;
-    auto kern = narrow_logpost_kernel<MODEL, B, TB>;
-    const int nc = narrow_block_chains(a.n_chains, sm_count), CP = nc + 1;
-    const size_t smem = sizeof(double) * ((size_t)3 * D * kNarrowTCH * CP + 1 + (size_t)2 * kNarrowTCH * a.CS);
+    auto kern = narrow_logpost_kernel<MODEL, B, TB, TCH, BPS>;
+    const int nc = narrow_block_chains(a.n_chains, sm_count, BPS == 1 ? kNarrowMaxChains : 128, BPS), CP = nc + 1;
+    const size_t smem = sizeof(double) * ((size_t)3 * D * TCH * CP + 1 + (size_t)2 * TCH * a.CS);
     static PerDeviceOnce once;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BPS == 1 ? 227 * 1024 : 56 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int blocks = (a.n_chains + nc - 1) / nc;

@@ -151,3 +151,22 @@ def test_narrow_kernel_guards_are_per_chain(pkg, monkeypatch):
     assert np.array_equal(ll[keep], ll0[keep]) and np.array_equal(g[keep], g0[keep])
     ll_ref, g_ref = H.oracle_batched(prob, bad)
     H.assert_parity(ll, g, ll_ref, g_ref, "guards")
+
+
+@pytest.mark.parametrize("b,nc", [(2, 8191), (2, 8192), (4, 32768)])
+def test_narrow_dispatch_is_seamless(pkg, monkeypatch, b, nc):
+    """Default dispatch for band half-widths <= 4: large batches run on K1-narrow (from 8192 chains for b <= 2, 32 768 for b = 3, 4),
+    through the chunked host path as well; same values to rounding as the windowed kernel, a sample against the oracle."""
+    monkeypatch.delenv("MAGI_K1", raising=False)
+    base = H.make_problem(model="fn", n=201, b=b, n_chains=8, seed=23, T=20.0, obs_every=5)
+    rng = np.random.default_rng(nc + b)
+    params = np.repeat(base["params"], (nc + 7) // 8, axis=0)[:nc] + 1e-3 * rng.normal(size=(nc, base["params"].shape[1]))
+    tg = H.cuda_target(pkg, base)
+    ll, g = tg.logdensity_and_gradient_batched(params)
+    idx = np.unique(np.concatenate([[0, nc // 2, nc - 1], rng.integers(0, nc, size=5)]))
+    ll_ref, g_ref = H.oracle_batched(base, params[idx])
+    H.assert_parity(ll[idx], g[idx], ll_ref, g_ref, "default dispatch, b=%d, %d chains" % (b, nc))
+    monkeypatch.setenv("MAGI_K1", "windowed")
+    tw = H.cuda_target(pkg, base)
+    llw, gw = tw.logdensity_and_gradient_batched(params)
+    H.assert_parity(ll, g, llw, gw, "default dispatch vs windowed, b=%d, %d chains" % (b, nc))
