@@ -15,11 +15,13 @@
 //   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x 128 chains is moved with coalesced
 //     128-byte row segments and transposed through shared memory (odd row pitch: conflict-free both ways), the gradient
 //     goes back the same way, so every state byte crosses HBM exactly once in each direction.
-// Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4.  What binds it in practice is the
-// coefficient broadcast: a warp-uniform 8- or 16-byte shared-memory load costs 2 / 4 wavefronts whatever the address pattern, i.e.
-// 2 wavefronts per coefficient and 32 chains: 8 D (2b+1) per step, 144 at b = 4 -- the tensor core of the DMMA kernels is, among
-// other things, the broadcast engine this kernel lacks.  Measured (FN n=201, 65 536 chains, one B200): b = 1 / 2 / 4 0.180 / 0.203 /
-// 0.306 ms against 0.414 ms for the windowed DMMA kernel (2350 / 2100 / 1395 GB/s algorithmic: 0.36 / 0.32 / 0.22 of the HBM peak).
+// Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4.  Measured (FN n=201, 65 536 chains, one
+// B200): b = 1 / 2 / 4 0.181 / 0.203 / 0.308 ms against 0.414 ms for the windowed DMMA kernel (2365 / 2105 / 1389 GB/s algorithmic:
+// 0.37 / 0.33 / 0.21 of the HBM peak).  What holds it there (ncu, profiles/narrow_b2_r02_v1_ncu_summary.txt, taken before the
+// last two changes): the registers of the windows allow 8 warps per SM; with them the issue slots are 49 % busy and the FP64 pipe
+// 25 %: 320 instructions per (warp, step) for 84 of FP64 at that point (index arithmetic of the staging loops, since removed;
+// two shared-memory loads per coefficient pair; register moves of the windows).  More warps at 128 registers and two chains per
+// thread sharing the coefficient loads were both measured slower (see narrow_launch_b).
 #pragma once
 #include <cmath>
 #include "magi_internal.cuh"
@@ -344,8 +346,8 @@ inline int narrow_block_chains(int n_chains, int sm_count, int max_chains, int b
 template <int MODEL, int B>
 static cudaError_t narrow_launch_b(const NarrowArgs& a, int sm_count, cudaStream_t st) {
     constexpr int TB = (B <= 2) ? 4 : 2;
-    // one 8-warp block per SM at up to 255 registers; four 4-warp blocks at 128 registers and 8-step chunks (BPS = 4) were measured
-    // slower (b = 1, 65 536 chains: 0.250 against 0.180 ms): the kernel is bound by shared-memory wavefronts, not by latency
+    // one 8-warp block per SM at up to 255 registers.  Measured slower: four 4-warp blocks at 128 registers and 8-step chunks (BPS = 4;
+    // b = 1, 65 536 chains: 0.250 against 0.180 ms), and two chains per thread sharing the coefficient loads (b = 1: 0.281 ms)
     constexpr int BPS = 1, TCH = 16;
     constexpr int D = Ode<MODEL>::D;
     auto kern = narrow_logpost_kernel<MODEL, B, TB, TCH, BPS>;
