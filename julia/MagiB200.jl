@@ -86,27 +86,31 @@ function logdensity_and_gradient_batched(t::MagiTargetGPU, params::Matrix{Float6
 end
 
 """
-    run_hmc_sampler(t, initial_params; n_samples, n_adapts, target_accept_ratio, initial_step_size, n_leapfrog, seed)
+    run_hmc_sampler(t, initial_params; n_samples, n_adapts, target_accept_ratio, initial_step_size, n_leapfrog, max_tree_depth, seed)
 
 Many chains at once with the state resident on the GPU (`magi_hmc_*`): the counterpart of `run_nuts_sampler`
 (src/samplers.jl:114-194) for a `P x n_chains` matrix of starting points.  `n_samples` is the total number of iterations
 including the `n_adapts` warm-up iterations, which are dropped.  Returns `(draws, accept_rate, step_size)` with
-`draws[:, chain, iteration]` = (theta..., sigma..., lp).
+`draws[:, chain, iteration]` = (theta..., sigma..., lp).  `max_tree_depth > 0` runs the reference's own trajectory
+(multinomial NUTS with the generalised U-turn criterion, src/samplers.jl:158-160) batched on the device (`magi_nuts_run`) instead of
+static trajectories of `n_leapfrog` steps.
 """
 function run_hmc_sampler(t::MagiTargetGPU, initial_params::Matrix{Float64}; n_samples::Int = 2000, n_adapts::Int = 1000,
                          target_accept_ratio::Float64 = 0.8, initial_step_size::Float64 = 0.1, n_leapfrog::Int = 20,
-                         seed::Integer = 0, chain_id_offset::Integer = 0, n_cols::Int)
+                         max_tree_depth::Int = 0, seed::Integer = 0, chain_id_offset::Integer = 0, n_cols::Int)
     @assert size(initial_params, 1) == t.P "Initial parameters dimension mismatch"        # samplers.jl:125
     nc = size(initial_params, 2)
     chk(rc, what) = rc == 0 || error(what * " failed: " * last_error())
     chk(ccall((:magi_hmc_init, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Culonglong, Cdouble, Clonglong),
               t.h, nc, initial_params, seed, initial_step_size, chain_id_offset), "magi_hmc_init")
-    n_adapts > 0 && chk(ccall((:magi_hmc_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}),
-                              t.h, n_adapts, n_leapfrog, 1, target_accept_ratio, 0, C_NULL), "magi_hmc_run (warm-up)")
+    # static trajectories: (n_iter, n_leapfrog, ...); NUTS: (n_iter, max_depth, ...) -- same argument list, two entry points
+    run(n_iter, adapt, store) = max_tree_depth > 0 ?
+        ccall((:magi_nuts_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}), t.h, n_iter, max_tree_depth, adapt, target_accept_ratio, store, C_NULL) :
+        ccall((:magi_hmc_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}), t.h, n_iter, n_leapfrog, adapt, target_accept_ratio, store, C_NULL)
+    n_adapts > 0 && chk(run(n_adapts, 1, 0), "sampler run (warm-up)")
     chk(ccall((:magi_hmc_reset_stats, LIB), Cint, (Ptr{Cvoid},), t.h), "magi_hmc_reset_stats")
     n_keep = n_samples - n_adapts
-    n_keep > 0 && chk(ccall((:magi_hmc_run, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cint, Ptr{Cvoid}),
-                            t.h, n_keep, n_leapfrog, 0, target_accept_ratio, 1, C_NULL), "magi_hmc_run")
+    n_keep > 0 && chk(run(n_keep, 0, 1), "sampler run")
     draws = Array{Float64}(undef, n_cols, nc, max(n_keep, 0))          # n_cols = n_params_ode + n_dims + 1
     stored = Ref{Clonglong}(0)
     chk(ccall((:magi_hmc_get_draws, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong, Ref{Clonglong}), t.h, draws, max(n_keep, 0), stored), "magi_hmc_get_draws")
