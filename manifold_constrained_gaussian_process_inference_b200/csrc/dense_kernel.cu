@@ -132,6 +132,116 @@ __global__ void __launch_bounds__(256) dense_grad_part_kernel(const DenseGradArg
     }
 }
 
+// ---- Lorenz-96 (D = 64) versions of the two pointwise stages.  The generic kernels above read every state value 4-5 times (one
+// block per (chain, dimension): 15 loads per point); a Lorenz-96 component couples only to its four neighbours, so
+//   * E: one thread per (chain, time) walks the dimensions with a rolling 4-value register window: one state load per point;
+//   * gradient: a block takes kL96Group consecutive dimensions of a chain and loads their kL96Group + 4 neighbouring state and KE
+//     values ONCE per time point; same thread <-> time mapping, same operation order and the same reduction tree as the generic
+//     kernel, hence the same bits. ----
+constexpr int kL96Group = 4;
+
+__global__ void __launch_bounds__(256) lorenz96_e_kernel(const double* __restrict__ params, long long pitch, int n, int D, int n_chains,
+                                                         const double* MX, double* E) {   // E may alias MX (in place)
+    const int c = blockIdx.x;
+    const double* xp = params + (size_t)c * pitch;
+    const double F = xp[(size_t)n * D];
+    const size_t plane = (size_t)n * n_chains;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+        const double* xi = xp + i;
+        double xm2 = xi[(size_t)(D - 2) * n], xm1 = xi[(size_t)(D - 1) * n], x0 = xi[0], xp1 = xi[(size_t)(1 % D) * n];
+        for (int d = 0; d < D; ++d) {
+            const size_t o = (size_t)d * plane + (size_t)c * n + i;
+            E[o] = ((xp1 - xm2) * xm1 - x0 + F) - MX[o];             // DenseOde<L96>::f, likelihoods.jl:130
+            xm2 = xm1; xm1 = x0; x0 = xp1;
+            xp1 = xi[(size_t)((d + 2) % D) * n];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) lorenz96_grad_group_kernel(const DenseGradArgs a) {
+    constexpr int G = kL96Group, NV = 5;                             // e.Ke, x.Cx, sse, bad flag, dF
+    __shared__ double sh[8][G * NV];
+    __shared__ double s_inv_sig2[G];
+    __shared__ int s_dim[G + 4];                                     // dimensions d0 - 2 .. d0 + G + 1 (cyclic)
+    const int c = blockIdx.x, d0 = blockIdx.y * G, n = a.n, D = a.D;
+    if (a.sigma_invalid) return;
+    const double* xp = a.params + (size_t)c * a.pitch;
+    double* gp = a.grad ? a.grad + (size_t)c * a.pitch : nullptr;
+    const size_t plane = (size_t)n * a.n_chains, base = (size_t)c * n;
+    const int nxt = n * D + 1;
+    const double inv_b1 = a.inv_beta[0], inv_b2 = a.inv_beta[1], inv_b3 = a.inv_beta[2];
+    if (threadIdx.x < G + 4) s_dim[threadIdx.x] = ((d0 - 2 + (int)threadIdx.x) % D + D) % D;
+    if (threadIdx.x < G) {
+        const int d = d0 + threadIdx.x < D ? d0 + threadIdx.x : D - 1;
+        double s;
+        if (a.sigma_is_fixed) s = a.sigma_init[d];
+        else {
+            const double raw = xp[nxt + d];
+            s = isnan(raw) ? raw : exp(fmin(fmax(raw, -15.0), 15.0));     // interface.jl:200
+        }
+        s_inv_sig2[threadIdx.x] = 1.0 / (s * s);
+    }
+    __syncthreads();
+    double acc[G][NV - 1];
+    unsigned badmask = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < NV - 1; ++j) acc[g][j] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double xr[G + 4], ker[G + 4];
+#pragma unroll
+        for (int k = 0; k < G + 4; ++k) {
+            const int dd = s_dim[k];
+            xr[k] = xp[(size_t)dd * n + i];
+            ker[k] = a.KE[(size_t)dd * plane + base + i];
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int d = d0 + g;
+            if (d < D) {
+                const size_t o = (size_t)d * plane + base + i;
+                const double xdv = xr[g + 2], y = a.yobs[(size_t)d * n + i], cx = a.CX[o], ke = ker[g + 2];
+                const bool fin = isfinite(y);
+                const double e0 = fin ? xdv - y : 0.0;
+                double gv = 0.0;
+                if (fin) gv -= (e0 * s_inv_sig2[g]) * inv_b3;        // likelihoods.jl:179
+                gv -= cx * inv_b2;                                   // :186
+                gv += a.MT[o] * inv_b1;                              // :194
+                gv -= xr[g] * (ker[g + 1] * inv_b1);                 // :214-216 with w = Ke / beta1 (:201); column d of the Jacobian: d f_{d-1} / d x_d = x_{d-2}
+                gv -= (-1.0) * (ker[g + 2] * inv_b1);                //   d f_d / d x_d = -1
+                gv -= (xr[g + 4] - xr[g + 1]) * (ker[g + 3] * inv_b1);   //   d f_{d+1} / d x_d = x_{d+2} - x_{d-1}
+                gv -= (-xr[g + 3]) * (ker[g + 4] * inv_b1);          //   d f_{d+2} / d x_d = -x_{d+1}
+                acc[g][3] -= ke * inv_b1;                            // :219-221 (d f_d / d F = 1)
+                acc[g][0] += a.E[o] * ke;
+                acc[g][1] += xdv * cx;
+                acc[g][2] += e0 * e0;
+                if (gp && !isfinite(gv)) badmask |= 1u << g;
+                if (gp) gp[(size_t)d * n + i] = gv;
+            }
+        }
+    }
+    const int wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            // part layout of the generic kernel: e.Ke, x.Cx, sse, bad flag, theta-gradient partial
+            double v = j < 3 ? acc[g][j] : (j == 3 ? (((badmask >> g) & 1u) ? 1.0 : 0.0) : acc[g][3]);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) sh[wp][g * NV + j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < G * NV) {
+        const int g = threadIdx.x / NV, j = threadIdx.x % NV;
+        if (d0 + g < D) {
+            double r = 0.0;
+            for (int i = 0; i < 8; ++i) r += sh[i][threadIdx.x];
+            a.part[((size_t)c * D + d0 + g) * NV + j] = r;
+        }
+    }
+}
+
 // Per chain: the log density in the reference's order of accumulation over the dimensions, sigma gradient, log-sigma
 // transform, guards (interface.jl:192-264); the per-dimension terms (log, divisions) are formed by D threads in parallel.
 template <int MODEL>
@@ -223,7 +333,8 @@ static int dense_pointwise(magi_handle* h, int n_chains, const double* params, l
                            const double* MX, double* E, const double* KE, const double* CX, const double* MT, int stage, cudaStream_t st) {
     if (stage == 0) {
         dim3 grid(n_chains, (h->n + 255) / 256);
-        dense_e_kernel<MODEL><<<grid, 256, 0, st>>>(params, pitch, h->n, h->D, n_chains, MX, E);
+        if constexpr (MODEL == MAGI_MODEL_L96) lorenz96_e_kernel<<<grid, 256, 0, st>>>(params, pitch, h->n, h->D, n_chains, MX, E);
+        else dense_e_kernel<MODEL><<<grid, 256, 0, st>>>(params, pitch, h->n, h->D, n_chains, MX, E);
     } else {
         DenseGradArgs a;
         a.n = h->n; a.D = h->D; a.K = h->K; a.P = h->P; a.n_chains = n_chains; a.sigma_is_fixed = h->sigma_is_fixed; a.sigma_invalid = h->sigma_invalid;
@@ -238,7 +349,8 @@ static int dense_pointwise(magi_handle* h, int n_chains, const double* params, l
             h->dense_part_cap = need;
         }
         a.part = h->d_dense_part;
-        dense_grad_part_kernel<MODEL><<<dim3(n_chains, h->D), 256, 0, st>>>(a);
+        if constexpr (MODEL == MAGI_MODEL_L96) lorenz96_grad_group_kernel<<<dim3(n_chains, (h->D + kL96Group - 1) / kL96Group), 256, 0, st>>>(a);
+        else dense_grad_part_kernel<MODEL><<<dim3(n_chains, h->D), 256, 0, st>>>(a);
         dense_finalize_kernel<MODEL><<<n_chains, 256, sizeof(double) * 4 * h->D, st>>>(a);
         h->launches++;
     }
