@@ -212,15 +212,17 @@ static int flow_groups_for(const magi_handle* h, int n_chains_call) {
     return 0;
 }
 
-// Band half-widths <= 4 of the two-component models: the FP64-FMA kernel (narrow_kernel.cuh) for batches that fill the machine
-// (one thread per chain sweeps the whole time axis: below ~8192 chains the DMMA kernels are faster -- FN n=201, b=2: 4096 chains
-// 0.049 against 0.036 ms, 16 384 chains 0.074 against 0.104 ms).  Like the other variants it is chosen by the size of the CALL (or
-// the sampler's global chain count), so how a batch is cut never changes the bits.
+// Band half-widths <= 4 of the two-component models: the FP64-FMA kernel (narrow_kernel.cuh) for batches that fill the machine.  One
+// thread per chain needs the whole sweep whatever the batch (FN n=201: 43 / 49 / 84 us at b = 1 / 2 / 4), the windowed DMMA kernel 36 us
+// per wave of 32 chains per SM: narrow wins where the windowed kernel needs a second wave (b <= 2) or a third one (b = 3, 4) --
+// measured: b = 2, 8192 chains 0.049 against 0.072 ms; b = 4, 16 384 chains 0.088 against 0.104 ms; 4096 chains 0.049 / 0.078 against
+// 0.036 ms.  Like the other variants it is chosen by the size of the CALL (or the sampler's global chain count), so how a batch is cut
+// never changes the bits.
 static bool narrow_route(const magi_handle* h, int n_chains_call) {
     if (h->narrow_mode < 0 || !narrow_supported(h->model, h->b)) return false;
     if (h->narrow_mode > 0) return true;
     const long long n_chains = h->dispatch_chains > 0 ? h->dispatch_chains : n_chains_call;
-    return n_chains >= (h->b <= 2 ? 8192 : 32768);
+    return n_chains > (h->b <= 2 ? 32LL : 64LL) * h->sm_count;
 }
 
 // The two kernels read differently ordered fragment tables (the windowed kernel permutes the output slots of a tile); one
