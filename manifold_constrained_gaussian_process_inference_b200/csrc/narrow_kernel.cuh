@@ -12,16 +12,16 @@
 //   * the band coefficients of a step are the same for every chain: a per-step table [s][m~@t1 | C~@t3 | K~@t2 | m~^T@t3 | y@t3]
 //     (built once per handle, zero where a row or a column falls off the time axis, 1/beta folded in) is staged per chunk of
 //     16 steps in shared memory and read with warp-uniform (broadcast) 16-byte loads: one wavefront per two coefficients;
-//   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x 128 chains is moved with coalesced
-//     128-byte row segments and transposed through shared memory (odd row pitch: conflict-free both ways), the gradient
-//     goes back the same way, so every state byte crosses HBM exactly once in each direction.
+//   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x up to 256 chains comes in as 128-byte
+//     row segments by cp.async (zero fill past the end of the axis / batch), double-buffered against the compute of the previous
+//     chunk, and is transposed through shared memory (odd row pitch: conflict-free both ways); the gradient goes back the same
+//     way, so every state byte crosses HBM exactly once in each direction.
 // Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4.  Measured (FN n=201, 65 536 chains, one
 // B200): b = 1 / 2 / 4 0.181 / 0.203 / 0.308 ms against 0.414 ms for the windowed DMMA kernel (2365 / 2105 / 1389 GB/s algorithmic:
-// 0.37 / 0.33 / 0.21 of the HBM peak).  What holds it there (ncu, profiles/narrow_b2_r02_v1_ncu_summary.txt, taken before the
-// last two changes): the registers of the windows allow 8 warps per SM; with them the issue slots are 49 % busy and the FP64 pipe
-// 25 %: 320 instructions per (warp, step) for 84 of FP64 at that point (index arithmetic of the staging loops, since removed;
-// two shared-memory loads per coefficient pair; register moves of the windows).  More warps at 128 registers and two chains per
-// thread sharing the coefficient loads were both measured slower (see narrow_launch_b).
+// 0.37 / 0.33 / 0.21 of the HBM peak).  What holds it there (profiles/narrow_b2_r02_ncu_summary.txt; timing-only ablations): 7-8 warps
+// per SM (the registers of the windows), issue slots 39 % busy, FP64 pipe 33 %; the copies in and out cost ~0.08 ms of a pass and
+// do not overlap with the compute (every warp issues its share of them between its steps); the coefficient loads cost nothing
+// measurable.  Tried and slower or without effect: DESIGN.md section 4, K1-narrow.
 #pragma once
 #include <cmath>
 #include "magi_internal.cuh"
