@@ -11,7 +11,7 @@
 //     TB steps are unrolled so that the windows move TB places at a time (one register move per value and TB steps);
 //   * the band coefficients of a step are the same for every chain: a per-step table [s][m~@t1 | C~@t3 | K~@t2 | m~^T@t3 | y@t3]
 //     (built once per handle, zero where a row or a column falls off the time axis, 1/beta folded in) is staged per chunk of
-//     16 steps in shared memory and read with warp-uniform (broadcast) 16-byte loads: one wavefront per two coefficients;
+//     16 steps in shared memory and read with warp-uniform (broadcast) 16-byte loads (two wavefronts per coefficient pair);
 //   * the chain state is chain-contiguous in HBM (the host layout): a chunk of 16 times x up to 256 chains comes in as 128-byte
 //     row segments by cp.async (zero fill past the end of the axis / batch), double-buffered against the compute of the previous
 //     chunk, and is transposed through shared memory (odd row pitch: conflict-free both ways); the gradient goes back the same
