@@ -85,38 +85,49 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// TCH: steps per staged chunk; BPS: blocks per SM (1: up to 256 chains per block and 255 registers; 4: 128 chains and 128 registers)
-template <int MODEL, int B, int TB, int TCH, int BPS>
-__global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow_logpost_kernel(const NarrowArgs a) {
+// TCH: steps per staged chunk.  Two organisations of the copies around the same arithmetic (a chain's result has the same bits in
+// both, so the choice between them is a matter of speed only):
+//   WS = false  every thread is a chain and issues its share of the copies between its steps: up to 256 chains per block, one block
+//               per SM, chunks of 16 steps, one gradient tile -- the fastest for batches of many waves at b <= 2;
+//   WS = true   WARP-SPECIALISED: the last warp of the block only moves data -- the next chunk's state and coefficient rows in, the
+//               previous chunk's gradient tile out -- while up to three compute warps (96 chains) work on the current chunk; one block
+//               barrier per chunk of 8 steps, two gradient tiles, two blocks per SM.  One staging warp keeps up with three compute
+//               warps, not with seven (7 + 1 warps: 0.30 ms at every b).  Faster for mid-size batches and for b = 3, 4.
+// Timing-only ablations of WS = false (FN n=201, 65 536 chains, ms with / without the copies): b = 2 0.210 / 0.128, b = 0 0.158 / 0.080;
+// without the coefficient loads 0.206 -- the copies, issued by the computing warps, are what does not overlap.
+template <int MODEL, int B, int TB, int TCH, bool WS>
+__global__ void __launch_bounds__(WS ? 128 : kNarrowMaxChains, WS ? 2 : 1) narrow_logpost_kernel(const NarrowArgs a) {
     using M = Ode<MODEL>;
     constexpr int D = M::D, K = M::K, KX = M::KX, W = 2 * B + 1, WP = W + 1;
     constexpr int XW = 4 * B + TB, EW = 2 * B + TB, CS = 4 * D * WP + 2 * D;        // = narrow_cs(D, B)
+    constexpr int NGS = WS ? 2 : 1;                                                 // gradient tiles
     static_assert(TCH % TB == 0, "chunk / unroll");
     extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x, NC = blockDim.x, CP = NC + 1, n = a.n;     // CP: odd row pitch of the transposed tiles
+    const int tid = threadIdx.x, NC = blockDim.x - (WS ? 32 : 0), CP = NC + 1, n = a.n;     // NC chains per block; CP: odd row pitch of the tiles
     double* xs0 = sm;                                  // [2 buffers][D][TCH][CP] state of a chunk's times
-    double* gs = xs0 + 2 * D * TCH * CP;               // [D][TCH][CP] gradient of the chunk's stage-3 times
-    double* cf0 = gs + D * TCH * CP;                   // [2 buffers][TCH][CS] (3 D TCH CP doubles before it: even, 16-byte aligned)
+    double* gs0 = xs0 + 2 * D * TCH * CP;              // [NGS buffers][D][TCH][CP] gradient of a chunk's stage-3 times
+    double* cf0 = gs0 + NGS * D * TCH * CP;            // [2 buffers][TCH][CS] ((2 + NGS) D TCH CP doubles before it: even, 16-byte aligned)
     const long long c0 = (long long)blockIdx.x * NC;
-    const long long c = c0 + tid;
-    const bool valid = c < a.n_chains;
-    const double* xp = a.params + (valid ? c : (long long)a.n_chains - 1) * a.pitch;
-    const int nxt = n * D + K;
     const int n_chunks = a.n_steps_pad / TCH;
-    // asynchronous stage-in of chunk ch (state of times [s0, s0 + TCH) as row segments of TCH doubles, zero past the end of the
-    // axis / of the batch; the chunk's coefficient rows) into buffer ch & 1
-    // Element idx = tid + k NC of a tile: time tt = idx % TCH and dimension (idx / TCH) % D do not depend on k (NC is a multiple of
-    // TCH D = 32), the chain advances by NC / (TCH D) per k: one running pointer per thread, no index arithmetic in the loops.
+    const bool want_grad = a.grad != nullptr;
+    // The copies are done by SN "stagers": every thread (WS = false) or the lanes of the staging warp.  Element idx = sid + k SN of
+    // a tile: time tt = idx % TCH and dimension (idx / TCH) % D do not depend on k (SN is a multiple of TCH D), the chain advances
+    // by SN / (TCH D) per k: one running pointer per stager, no index arithmetic in the loops.
     static_assert(TCH * D <= 32 && 32 % (TCH * D) == 0, "tile mapping");
-    const int m_tt = tid % TCH, m_d = (tid / TCH) % D, m_cl = tid / (TCH * D), m_step = NC / (TCH * D), m_iter = TCH * D;
+    const int SN = WS ? 32 : NC, sid = WS ? tid - NC : tid;        // (sid < 0: a compute thread of the warp-specialised kernel, copies nothing)
+    const int sidc = sid < 0 ? 0 : sid;
+    const int m_tt = sidc % TCH, m_d = (sidc / TCH) % D, m_cl = sidc / (TCH * D);
+    const int m_step = SN / (TCH * D), m_iter = WS ? NC * D * TCH / 32 : TCH * D;      // (copies per stager and tile: a constant when every thread copies)
     const int m_soff = (m_d * TCH + m_tt) * CP + m_cl;
+    // asynchronous copy of chunk ch (state of times [s0, s0 + TCH) as row segments of TCH doubles, zero past the end of the axis / of
+    // the batch; the chunk's coefficient rows) into buffer ch & 1
     auto stage_in = [&](int ch) {
         const int s0 = ch * TCH, t = s0 + m_tt;
         double* xs = xs0 + (ch & 1) * D * TCH * CP + m_soff;
         const bool tok = t < n;
-        const long long rows_left = (long long)a.n_chains - c0 - m_cl;           // chains from this thread's first one to the end of the batch
-        const double* src = a.params + (c0 + m_cl) * a.pitch + (long long)m_d * n + (tok ? t : 0);
+        const long long rows_left = (long long)a.n_chains - c0 - m_cl;       // chains from this stager's first one to the end of the batch
         const long long sstep = (long long)m_step * a.pitch;
+        const double* src = a.params + (c0 + m_cl) * a.pitch + (long long)m_d * n + (tok ? t : 0);
 #pragma unroll 4
         for (int k = 0; k < m_iter; ++k) {
             const bool ok = tok && (long long)k * m_step < rows_left;
@@ -125,10 +136,61 @@ __global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow
         }
         const double* csrc = a.steptab + (size_t)s0 * CS;
         double* dst = cf0 + (ch & 1) * TCH * CS;
-        for (int idx = tid; idx < TCH * CS / 2; idx += NC) cp_async16(dst + 2 * idx, csrc + 2 * idx);
+        for (int idx = sid; idx < TCH * CS / 2; idx += SN) cp_async16(dst + 2 * idx, csrc + 2 * idx);
         cp_async_commit();
     };
-    stage_in(0);
+    // gradient of chunk ch (times [s0 - 3B, s0 + TCH - 3B)) from its tile to global memory
+    auto stage_out = [&](int ch) {
+        const int t = ch * TCH + m_tt - 3 * B;
+        if (t < 0 || t >= n) return;
+        const long long rows_left = (long long)a.n_chains - c0 - m_cl;
+        const long long sstep = (long long)m_step * a.pitch;
+        double* dst = a.grad + (c0 + m_cl) * a.pitch + (long long)m_d * n + t;
+        const double* g = gs0 + (ch & (NGS - 1)) * D * TCH * CP + m_soff;
+        if constexpr (WS) {
+#pragma unroll 1
+            for (int k0 = 0; k0 < m_iter; k0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = (k0 + k < m_iter) ? g[(k0 + k) * m_step] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k0 + k < m_iter && (long long)(k0 + k) * m_step < rows_left) dst[(k0 + k) * sstep] = v[k];
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < m_iter; ++k) {
+                if ((long long)k * m_step < rows_left) *dst = g[k * m_step];
+                dst += sstep;
+            }
+        }
+    };
+    if constexpr (WS) {
+        if (tid >= NC) {
+            // ---------------- the staging warp ----------------
+            stage_in(0);
+            cp_async_wait_all();
+            __syncthreads();
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                if (ch + 1 < n_chunks) stage_in(ch + 1);       // its buffer was last read in iteration ch - 1
+                if (ch >= 1 && want_grad) stage_out(ch - 1);    // written in iteration ch - 1, rewritten in iteration ch + 1
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            if (want_grad) stage_out(n_chunks - 1);
+            __syncthreads();       // every x-gradient store of the block is issued before a guard of the compute warps overwrites a chain's row
+            return;
+        }
+    } else {
+        stage_in(0);
+    }
+
+    // ---------------- one thread per chain ----------------
+    const long long c = c0 + tid;
+    const bool valid = c < a.n_chains;
+    const double* xp = a.params + (valid ? c : (long long)a.n_chains - 1) * a.pitch;
+    const int nxt = n * D + K;
 
     double th[KX];
 #pragma unroll
@@ -160,16 +222,19 @@ __global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow
 #pragma unroll
     for (int i = 0; i < K; ++i) gth[i] = 0.0;
     bool bad = false;
-    const bool want_grad = a.grad != nullptr;
 
+    if constexpr (WS) __syncthreads();       // chunk 0 is in shared memory
 #pragma unroll 1
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int s0 = ch * TCH;
-        cp_async_wait_all();
-        __syncthreads();                     // chunk ch is in shared memory; everybody is done with chunk ch - 1 (its buffer, its gradient tile)
-        if (ch + 1 < n_chunks) stage_in(ch + 1);
+        if constexpr (!WS) {
+            cp_async_wait_all();
+            __syncthreads();                 // chunk ch is in shared memory; everybody is done with chunk ch - 1 (its buffer, its gradient tile)
+            if (ch + 1 < n_chunks) stage_in(ch + 1);
+        }
         const double* xs = xs0 + (ch & 1) * D * TCH * CP;
         const double* cf = cf0 + (ch & 1) * TCH * CS;
+        double* gs = gs0 + (ch & (NGS - 1)) * D * TCH * CP;
 #pragma unroll 1
         for (int sb = 0; sb < TCH / TB; ++sb) {
             // Stage-major over the TB unrolled steps: the TB band products of a stage are independent dependency chains (a
@@ -254,22 +319,8 @@ __global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow
                 for (int i = 0; i < EW - TB; ++i) { ew[d][i] = ew[d][i + TB]; kw[d][i] = kw[d][i + TB]; }
             }
         }
-        __syncthreads();
-        // ---- stage out: gradient of times [s0 - 3B, s0 + TCH - 3B) ----
-        if (want_grad) {
-            const int t = s0 + m_tt - 3 * B;
-            if (t >= 0 && t < n) {
-                const long long rows_left = (long long)a.n_chains - c0 - m_cl;
-                double* dst = a.grad + (c0 + m_cl) * a.pitch + (long long)m_d * n + t;
-                const long long sstep = (long long)m_step * a.pitch;
-                const double* g = gs + m_soff;
-#pragma unroll 4
-                for (int k = 0; k < m_iter; ++k) {
-                    if ((long long)k * m_step < rows_left) *dst = g[k * m_step];
-                    dst += sstep;
-                }
-            }
-        }
+        __syncthreads();                     // WS: chunk ch + 1 has arrived, the staging warp may take this chunk's gradient tile
+        if constexpr (!WS) { if (want_grad) stage_out(ch); }
     }
     __syncthreads();       // every x-gradient store of the block is issued before a guard below overwrites a chain's row
 
@@ -331,36 +382,48 @@ __global__ void __launch_bounds__(BPS == 1 ? kNarrowMaxChains : 128, BPS) narrow
     }
 }
 
-// Chains per block: one block per SM (its tiles take most of the shared memory), so the batch should come in whole waves of
-// sm_count blocks -- the multiple of 32 that needs the fewest waves, the larger one on a tie (more warps per SM).
-inline int narrow_block_chains(int n_chains, int sm_count, int max_chains, int bps) {
+// Chains per block: the multiple of 32 (at most max_chains) that needs the fewest waves of slots = blocks-per-SM x sm_count blocks, the
+// larger one on a tie.
+inline int narrow_block_chains(int n_chains, long long slots, int max_chains) {
     int best = 32; long long best_cost = -1;
     for (int nc = 32; nc <= max_chains; nc += 32) {
-        const long long tiles = (n_chains + nc - 1) / nc, waves = (tiles + (long long)sm_count * bps - 1) / ((long long)sm_count * bps);
+        const long long tiles = (n_chains + nc - 1) / nc, waves = (tiles + slots - 1) / slots;
         const long long cost = waves * (100 + nc);          // a wave of wider blocks takes longer, but far less than proportionally
         if (best_cost < 0 || cost <= best_cost) { best = nc; best_cost = cost; }
     }
     return best;
 }
 
-template <int MODEL, int B>
-static cudaError_t narrow_launch_b(const NarrowArgs& a, int sm_count, cudaStream_t st) {
-    constexpr int TB = (B <= 2) ? 4 : 2;
-    // one 8-warp block per SM at up to 255 registers.  Measured slower: four 4-warp blocks at 128 registers and 8-step chunks (BPS = 4;
-    // b = 1, 65 536 chains: 0.250 against 0.180 ms), and two chains per thread sharing the coefficient loads (b = 1: 0.281 ms)
-    constexpr int BPS = 1, TCH = 16;
+template <int MODEL, int B, bool WS>
+static cudaError_t narrow_launch_ws(const NarrowArgs& a, int sm_count, cudaStream_t st) {
+    constexpr int TB = (B <= 2) ? 4 : 2, TCH = WS ? 8 : 16;
     constexpr int D = Ode<MODEL>::D;
-    auto kern = narrow_logpost_kernel<MODEL, B, TB, TCH, BPS>;
-    const int nc = narrow_block_chains(a.n_chains, sm_count, BPS == 1 ? kNarrowMaxChains : 128, BPS), CP = nc + 1;
-    const size_t smem = sizeof(double) * ((size_t)3 * D * TCH * CP + 1 + (size_t)2 * TCH * a.CS);
+    auto kern = narrow_logpost_kernel<MODEL, B, TB, TCH, WS>;
+    const int nc = WS ? narrow_block_chains(a.n_chains, 2LL * sm_count, 96) : narrow_block_chains(a.n_chains, sm_count, kNarrowMaxChains);
+    const int CP = nc + 1;
+    const size_t smem = sizeof(double) * ((size_t)(WS ? 4 : 3) * D * TCH * CP + (size_t)2 * TCH * a.CS);
     static PerDeviceOnce once;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BPS == 1 ? 227 * 1024 : 56 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS ? 100 * 1024 : 227 * 1024);
         if (e != cudaSuccess) return e;
     }
     const int blocks = (a.n_chains + nc - 1) / nc;
-    kern<<<blocks, nc, smem, st>>>(a);
+    kern<<<blocks, nc + (WS ? 32 : 0), smem, st>>>(a);
     return cudaGetLastError();
+}
+
+// Which organisation (measured, FN n=201, one B200, ms at 8192 / 16 384 / 65 536 chains; WS = false | true):
+//   b = 1:  0.043 / 0.068 / 0.187  |  0.037 / 0.068 / 0.199        b = 2:  0.051 / 0.076 / 0.217  |  0.039 / 0.072 / 0.248
+//   b = 4:  0.084 / 0.091 / 0.306  |  0.070 / 0.113 / 0.280
+// Other tries, slower: four 4-warp blocks per SM at 128 registers (b = 1: 0.250), two chains per thread sharing the coefficient loads
+// (b = 1: 0.281 ms, with half the warps), 7 + 1 warps (0.30 ms at every b).
+template <int MODEL, int B>
+static cudaError_t narrow_launch_b(const NarrowArgs& a, int sm_count, cudaStream_t st) {
+    const long long per_sm = (a.n_chains + sm_count - 1) / sm_count;
+    // chains per SM: the warp-specialised kernel up to its own first wave (2 x 96; b >= 3: while 64-chain blocks do), and for b >= 3
+    // again beyond one wave of the other (b = 4: 32 768 chains 0.153 | 0.211 ms, 65 536 chains 0.306 | 0.281)
+    const bool ws = (B >= 3) ? (per_sm <= 64 || per_sm > 256) : per_sm <= 96;
+    return ws ? narrow_launch_ws<MODEL, B, true>(a, sm_count, st) : narrow_launch_ws<MODEL, B, false>(a, sm_count, st);
 }
 
 template <int MODEL>
