@@ -17,11 +17,12 @@
 //     chunk, and is transposed through shared memory (odd row pitch: conflict-free both ways); the gradient goes back the same
 //     way, so every state byte crosses HBM exactly once in each direction.
 // Roofline: HBM for b <= 2, FP64 (DFMA, the same pipe as DMMA on this chip) for b = 3, 4.  Measured (FN n=201, 65 536 chains, one
-// B200): b = 1 / 2 / 4 0.181 / 0.203 / 0.308 ms against 0.414 ms for the windowed DMMA kernel (2365 / 2105 / 1389 GB/s algorithmic:
-// 0.37 / 0.33 / 0.21 of the HBM peak).  What holds it there (profiles/narrow_b2_r02_ncu_summary.txt; timing-only ablations): 7-8 warps
-// per SM (the registers of the windows), issue slots 39 % busy, FP64 pipe 33 %; the copies in and out cost ~0.08 ms of a pass and
-// do not overlap with the compute (every warp issues its share of them between its steps); the coefficient loads cost nothing
-// measurable.  Tried and slower or without effect: DESIGN.md section 4, K1-narrow.
+// B200, bench.py -> smallband): b = 1 / 2 / 4 0.185 / 0.214 / 0.281 ms against 0.414 ms for the windowed DMMA kernel = 0.36 / 0.31 / 0.24
+// of the HBM peak.  What holds it there (profiles/narrow_b2_r02_ncu_summary.txt; timing-only ablations): 7-8 warps per SM (the
+// registers of the windows), issue slots 39 % busy, FP64 pipe 33 %; the copies in and out cost ~0.08 ms of a pass and do not
+// overlap with the compute when every warp issues its share of them between its steps; the coefficient loads cost nothing
+// measurable.  Hence the second, warp-specialised organisation of the copies (template flag WS below).  Tried and slower or
+// without effect: DESIGN.md section 4, K1-narrow.
 #pragma once
 #include <cmath>
 #include "magi_internal.cuh"

@@ -153,9 +153,10 @@ def test_narrow_kernel_guards_are_per_chain(pkg, monkeypatch):
     H.assert_parity(ll, g, ll_ref, g_ref, "guards")
 
 
-@pytest.mark.parametrize("b,nc", [(2, 32 * 148), (2, 32 * 148 + 1), (4, 64 * 148), (4, 64 * 148 + 1)])
+@pytest.mark.parametrize("b,nc", [(2, 32 * 148), (2, 32 * 148 + 1), (4, 64 * 148), (4, 64 * 148 + 1), (2, 96 * 148 + 5), (1, 40000), (4, 257 * 148)])
 def test_narrow_dispatch_is_seamless(pkg, monkeypatch, b, nc):
-    """Default dispatch for band half-widths <= 4: large batches run on K1-narrow (beyond 32 chains per SM for b <= 2, 64 per SM for b = 3, 4),
+    """Default dispatch for band half-widths <= 4: large batches run on K1-narrow (beyond 32 chains per SM for b <= 2, 64 per SM for b = 3, 4; its two organisations of the copies --
+    warp-specialised up to 96 chains per SM, every thread copying beyond -- on either side of their own seams),
     through the chunked host path as well; same values to rounding as the windowed kernel, a sample against the oracle."""
     monkeypatch.delenv("MAGI_K1", raising=False)
     base = H.make_problem(model="fn", n=201, b=b, n_chains=8, seed=23, T=20.0, obs_every=5)
